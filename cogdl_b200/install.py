@@ -1,0 +1,61 @@
+"""Register the sm_100a backend inside an importable `cogdl` package (the drop-in step).
+
+Plug-in point: the module-global dict `cogdl.utils.spmm_utils.CONFIGS` and the
+`cogdl.operators.*` module attributes; layer modules capture the callables at construction
+(SpMM.__init__ cogdl/utils/spmm_utils.py:131, EdgeSoftmax.__init__ :195, MultiHeadSpMM.__init__
+:234-235, MaxAggregator.__init__ cogdl/layers/sage_layer.py:22-25), so call install() BEFORE
+building models.  Two levels are patched:
+
+  1. operator level -- CONFIGS["fast_spmm" | "csr_edge_softmax" | "csrmhspmm" | "fused_gat_func"]
+     and cogdl.operators.{spmm.csrspmm, edge_softmax.csr_edge_softmax, mhspmm.csrmhspmm,
+     scatter_max.scatter_max, fused_gat.fused_gat_func}, with the *_flag latches set so the lazy
+     initialisers do not overwrite them;
+  2. dispatch level -- every already-imported cogdl module attribute that IS the reference's
+     spmm / edge_softmax / mh_spmm / fused_gat_op function (or SpMM / EdgeSoftmax / MultiHeadSpMM
+     / FusedGATOp class) is rebound to this package's version, which keeps the int32 CSR, hub
+     plan and transpose cached on the graph instead of re-casting per call.
+"""
+import sys
+
+
+def install(rebind_dispatch=True):
+    import cogdl.utils.spmm_utils as ref_su  # raises ImportError if cogdl is not importable
+
+    from . import operators as ops
+    from .utils import spmm_utils as su
+
+    ref_su.CONFIGS.update({
+        "fast_spmm": ops.csrspmm, "csr_edge_softmax": ops.csr_edge_softmax, "csrmhspmm": ops.csrmhspmm,
+        "fused_gat_func": ops.fused_gat_func,
+        "spmm_flag": True, "mh_spmm_flag": True, "fused_gat_flag": True,
+    })
+    import importlib
+
+    for mod_name, attrs in (
+        ("cogdl.operators.spmm", {"csrspmm": ops.csrspmm}),
+        ("cogdl.operators.edge_softmax", {"csr_edge_softmax": ops.csr_edge_softmax}),
+        ("cogdl.operators.mhspmm", {"csrmhspmm": ops.csrmhspmm}),
+        ("cogdl.operators.scatter_max", {"scatter_max": ops.scatter_max}),
+        ("cogdl.operators.fused_gat", {"fused_gat_func": ops.fused_gat_func}),
+    ):
+        try:
+            mod = importlib.import_module(mod_name)
+        except Exception:  # the reference module itself may fail to JIT-build; create the attribute anyway
+            continue
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+
+    patched = []
+    if rebind_dispatch:
+        names = ["spmm", "edge_softmax", "mh_spmm", "fused_gat_op", "check_fused_gat", "SpMM", "EdgeSoftmax",
+                 "MultiHeadSpMM", "FusedGATOp"]
+        originals = {id(getattr(ref_su, n)): getattr(su, n) for n in names if hasattr(ref_su, n)}
+        for mname, mod in list(sys.modules.items()):
+            if mod is None or not (mname == "cogdl" or mname.startswith("cogdl.")):
+                continue
+            for attr, val in list(vars(mod).items()):
+                new = originals.get(id(val))
+                if new is not None and val is not new:
+                    setattr(mod, attr, new)
+                    patched.append(f"{mname}.{attr}")
+    return patched

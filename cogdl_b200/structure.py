@@ -1,0 +1,178 @@
+"""Device-resident CSR structure in the kernels' format (int32), with everything that is derived
+from the structure alone cached next to it: the hub plan and the transpose (CSC + permutation).
+
+Why this exists: the reference re-casts `row_ptr.int(), col_indices.int()` on EVERY spmm call
+(cogdl/utils/spmm_utils.py:106) and re-runs cuSPARSE csr2csc on EVERY backward of a non-symmetric
+graph (cogdl/operators/spmm.py:67).  Here both are computed once per structure.
+
+All device work goes through the C ABI (cogdl_b200._cabi); torch only owns the memory.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _cabi
+
+DEFAULT_CHUNK_EDGES = 256
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    """No CPU fallback: fail loudly when handed a CPU tensor (the reference silently takes a
+    slow torch path, cogdl/operators/spmm.py:11-40 `except Exception: csrspmm = None`)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "cogdl_b200 operators run on CUDA (sm_100a) only and have no CPU fallback; "
+                f"got a tensor on {t.device}"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+class HubPlan:
+    """Which rows are cut into edge chunks (see cogdl_b200_hub_plan_t in include/cogdl_b200.h)."""
+
+    def __init__(self, rowptr32, chunk_edges=DEFAULT_CHUNK_EDGES):
+        dev = rowptr32.device
+        n_rows = rowptr32.numel() - 1
+        self.chunk_edges = int(chunk_edges)
+        self.device = dev
+        with torch.cuda.device(dev):
+            counts = torch.empty(2, dtype=torch.int32, device=dev)
+            _cabi.call("cogdl_b200_hub_plan_count", _ptr(rowptr32), n_rows, self.chunk_edges, _ptr(counts), _stream(dev))
+            n_hub, n_chunks = (int(v) for v in counts.tolist())  # one sync per structure
+            self.n_hub_rows, self.n_chunks = n_hub, n_chunks
+            self.hub_rows = torch.empty(max(n_hub, 1), dtype=torch.int32, device=dev)
+            self.chunks = torch.empty(max(2 * n_chunks, 2), dtype=torch.int32, device=dev)
+            self.counters = torch.zeros(max(n_chunks, 1), dtype=torch.int32, device=dev)
+            if n_chunks > 0:
+                _cabi.call("cogdl_b200_hub_plan_fill", _ptr(rowptr32), n_rows, self.chunk_edges, _ptr(counts),
+                           _ptr(self.hub_rows), _ptr(self.chunks), _stream(dev))
+
+    def struct(self, partial_bytes=0):
+        """ctypes struct for one call; partial scratch comes from torch's caching allocator.
+        Returns (struct, keepalive)."""
+        s = _cabi.HubPlanStruct()
+        s.chunk_edges = self.chunk_edges
+        s.n_hub_rows = self.n_hub_rows
+        s.n_chunks = self.n_chunks
+        s.hub_rows = self.hub_rows.data_ptr()
+        s.chunks = self.chunks.data_ptr()
+        s.counters = self.counters.data_ptr()
+        scratch = None
+        if self.n_chunks > 0 and partial_bytes > 0:
+            scratch = torch.empty((partial_bytes + 15) // 16 * 4, dtype=torch.float32, device=self.device)
+            s.partials = scratch.data_ptr()
+            s.partials_bytes = scratch.numel() * 4
+        return s, scratch
+
+
+class CSRStructure:
+    """int32 CSR on the device + cached hub plan + cached transpose."""
+
+    def __init__(self, rowptr32, colind32, n_cols=None, chunk_edges=DEFAULT_CHUNK_EDGES):
+        dev = require_cuda(rowptr32, colind32)
+        if rowptr32.dtype != torch.int32 or colind32.dtype != torch.int32:
+            raise ValueError("rowptr / colind must be int32 (use CSRStructure.from_int64 for Graph tensors)")
+        if not (rowptr32.is_contiguous() and colind32.is_contiguous()):
+            raise ValueError("rowptr / colind must be contiguous")
+        self.rowptr, self.colind = rowptr32, colind32
+        self.device = dev
+        self.n_rows = rowptr32.numel() - 1
+        self.nnz = colind32.numel()
+        self.n_cols = self.n_rows if n_cols is None else int(n_cols)
+        self.chunk_edges = int(chunk_edges)
+        self._plan = None
+        self._csc = None
+
+    @staticmethod
+    def from_int64(row_ptr, col, n_cols=None, chunk_edges=DEFAULT_CHUNK_EDGES):
+        """Narrow Graph-style int64 (row_ptr, col) once, on the device."""
+        dev = require_cuda(row_ptr, col)
+        if row_ptr.dtype == torch.int32 and col.dtype == torch.int32:
+            return CSRStructure(row_ptr.contiguous(), col.contiguous(), n_cols, chunk_edges)
+        if row_ptr.dtype != torch.int64 or col.dtype != torch.int64:
+            raise ValueError("row_ptr / col must both be int64 or both be int32")
+        if col.numel() >= 2**31 or row_ptr.numel() >= 2**31:
+            raise ValueError("graph too large for int32 indices on one device")
+        row_ptr, col = row_ptr.contiguous(), col.contiguous()
+        rp = torch.empty(row_ptr.numel(), dtype=torch.int32, device=dev)
+        ci = torch.empty(col.numel(), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("cogdl_b200_narrow_i64_i32", _ptr(row_ptr), _ptr(rp), row_ptr.numel(), _stream(dev))
+            _cabi.call("cogdl_b200_narrow_i64_i32", _ptr(col), _ptr(ci), col.numel(), _stream(dev))
+        return CSRStructure(rp, ci, n_cols, chunk_edges)
+
+    @property
+    def plan(self):
+        if self._plan is None:
+            self._plan = HubPlan(self.rowptr, self.chunk_edges)
+        return self._plan
+
+    def plan_struct(self, partial_bytes=0):
+        """(ctypes pointer or None, keepalive) for one kernel call."""
+        if self.chunk_edges <= 0:
+            return None, None
+        s, scratch = self.plan.struct(partial_bytes)
+        return ctypes.byref(s), (s, scratch)
+
+    def csc(self):
+        """(CSRStructure of A^T, perm) with perm[q] = CSR position of CSC entry q.  Cached."""
+        if self._csc is None:
+            dev = self.device
+            with torch.cuda.device(dev):
+                colptr = torch.empty(self.n_cols + 1, dtype=torch.int32, device=dev)
+                rowind = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+                perm = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+                wbytes = int(_cabi.load().cogdl_b200_csr2csc_workspace_bytes(self.nnz, self.n_cols))
+                ws = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
+                _cabi.call("cogdl_b200_csr2csc", _ptr(self.rowptr), _ptr(self.colind), self.n_rows, self.n_cols,
+                           self.nnz, _ptr(colptr), _ptr(rowind), _ptr(perm), _ptr(ws), ws.numel(), _stream(dev))
+            t = CSRStructure(colptr, rowind, n_cols=self.n_rows, chunk_edges=self.chunk_edges)
+            self._csc = (t, perm)
+        return self._csc
+
+
+# ---------------------------------------------------------------------------------------------
+# Structure cache for the operator-level API, where the caller hands us bare (rowptr, colind)
+# tensors (reference signature csrspmm(rowptr, colind, x, csr_data, sym), operators/spmm.py:24).
+# Keyed on storage identity; the key tensors are kept alive by the entry so an address cannot be
+# recycled under a live key, and the in-place version counter catches mutation.
+# ---------------------------------------------------------------------------------------------
+_CACHE = OrderedDict()
+_CACHE_CAP = 32
+
+
+def structure_for(rowptr, colind, n_cols=None):
+    key = (rowptr.data_ptr(), colind.data_ptr(), rowptr.numel(), colind.numel(), str(rowptr.device),
+           rowptr.dtype, n_cols)
+    ent = _CACHE.get(key)
+    if ent is not None:
+        st, rp, ci, ver = ent
+        if ver == (rp._version, ci._version):
+            _CACHE.move_to_end(key)
+            return st
+    st = CSRStructure.from_int64(rowptr, colind, n_cols)
+    _CACHE[key] = (st, rowptr, colind, (rowptr._version, colind._version))
+    if len(_CACHE) > _CACHE_CAP:
+        _CACHE.popitem(last=False)
+    return st
+
+
+def clear_structure_cache():
+    _CACHE.clear()

@@ -1,0 +1,167 @@
+"""Dispatch layer -- same public names, signatures and semantics as cogdl/utils/spmm_utils.py:
+
+    spmm(graph, x, actnn=False, fast_spmm=None, fast_spmm_cpu=None)            :85
+    edge_softmax(graph, edge_val, csr_edge_softmax=None)                       :172
+    mh_spmm(graph, attention, h, csrmhspmm=None, fast_spmm=None)               :201
+    fused_gat_op(attn_row, attn_col, graph, negative_slope, in_feat, fused_gat_func=None)   :251
+    modules SpMM / EdgeSoftmax / MultiHeadSpMM / FusedGATOp, registry CONFIGS  :4-14
+
+Differences (deliberate):
+  * one backend only -- the sm_100a kernels.  There is no `spmm_scatter` / `spmm_cpu` /
+    `edge_softmax_val` fallback: a CPU tensor raises instead of silently taking a slow path;
+  * the int32 CSR, hub plan and transpose come from `graph.structure()` (cached on the
+    Adjacency) instead of `row_ptr.int(), col_indices.int()` on every call (:106);
+  * `out_norm` / `in_norm` are applied around the kernel exactly as the reference does (:99-109).
+`fast_spmm=` / `csr_edge_softmax=` / `csrmhspmm=` overrides are honoured (the reference's A/B
+injection point); the `grb_adj` short-circuit (:86-91) is kept.
+"""
+import torch
+
+from ..operators import csrspmm, csr_edge_softmax, csrmhspmm, fused_gat_func
+from ..operators.spmm import SPMMFunction
+from ..operators.edge_softmax import EdgeSoftmaxFunction
+from ..operators.mhspmm import MHSPMMFunction
+from ..operators.fused_gat import FusedGATFunction
+
+CONFIGS = {
+    "fast_spmm": csrspmm,
+    "csrmhspmm": csrmhspmm,
+    "csr_edge_softmax": csr_edge_softmax,
+    "fused_gat_func": fused_gat_func,
+    "fast_spmm_cpu": None,     # no CPU path in this package
+    "spmm_flag": True,
+    "mh_spmm_flag": True,
+    "fused_gat_flag": True,
+    "spmm_cpu_flag": True,
+}
+
+
+def initialize_spmm():
+    return None
+
+
+def initialize_edge_softmax():
+    return None
+
+
+def initialize_fused_gat():
+    return None
+
+
+def check_fused_gat():
+    return CONFIGS["fused_gat_func"] is not None
+
+
+def _structure(graph):
+    if hasattr(graph, "structure"):
+        return graph.structure()
+    # a real cogdl.data.Graph: cache our structure on its adjacency object
+    adj = graph._adj
+    st = adj.__dict__.get("_b200_structure")
+    key = (graph.row_indptr.data_ptr(), graph.col_indices.data_ptr())
+    if st is None or st[0] != key:
+        from ..structure import CSRStructure
+
+        st = (key, CSRStructure.from_int64(graph.row_indptr, graph.col_indices, n_cols=graph.num_nodes))
+        adj.__dict__["_b200_structure"] = st
+    return st[1]
+
+
+def spmm(graph, x, actnn=False, fast_spmm=None, fast_spmm_cpu=None):
+    if getattr(graph, "grb_adj", None) is not None:
+        if graph.grb_adj.is_sparse:
+            return torch.sparse.mm(graph.grb_adj, x)
+        return torch.mm(graph.grb_adj, x)
+    if not x.is_cuda:
+        raise RuntimeError("cogdl_b200.spmm: CPU tensors are not supported (no CPU fallback); move the graph and "
+                           "features to a B200 device")
+    if graph.out_norm is not None:
+        x = graph.out_norm.to(x.device) * x
+    csr_data = graph.raw_edge_weight
+    if x.dtype == torch.half:
+        csr_data = csr_data.half()
+    if fast_spmm is not None and fast_spmm is not csrspmm:
+        x = fast_spmm(graph.row_indptr.int(), graph.col_indices.int(), x, csr_data, graph.is_symmetric(), actnn=actnn)
+    else:
+        if actnn:
+            raise NotImplementedError("actnn=True is not supported by cogdl_b200")
+        x = SPMMFunction.apply(_structure(graph), None, x, csr_data, graph.is_symmetric())
+    if graph.in_norm is not None:
+        x = graph.in_norm.to(x.device) * x
+    return x
+
+
+class SpMM(torch.nn.Module):
+    def __init__(self, actnn=False):
+        super().__init__()
+        self.actnn = actnn
+        self.fast_spmm = CONFIGS["fast_spmm"]
+
+    def forward(self, graph, x):
+        return spmm(graph, x, self.actnn, self.fast_spmm)
+
+
+def edge_softmax(graph, edge_val, csr_edge_softmax=None):
+    if not edge_val.is_cuda:
+        raise RuntimeError("cogdl_b200.edge_softmax: CPU tensors are not supported (no CPU fallback)")
+    flat = edge_val.dim() == 1
+    if flat:
+        edge_val = edge_val.view(-1, 1)
+    if csr_edge_softmax is not None and csr_edge_softmax is not CONFIGS["csr_edge_softmax"]:
+        val = csr_edge_softmax(graph.row_indptr.int(), edge_val)
+    else:
+        val = EdgeSoftmaxFunction.apply(_structure(graph), edge_val)
+    return val.view(-1) if flat else val
+
+
+class EdgeSoftmax(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.csr_edge_softmax = CONFIGS["csr_edge_softmax"]
+
+    def forward(self, graph, edge_val):
+        return edge_softmax(graph, edge_val, self.csr_edge_softmax)
+
+
+def mh_spmm(graph, attention, h, csrmhspmm=None, fast_spmm=None):
+    if not h.is_cuda:
+        raise RuntimeError("cogdl_b200.mh_spmm: CPU tensors are not supported (no CPU fallback)")
+    nhead = h.shape[1]
+    if nhead > 1:
+        if csrmhspmm is not None and csrmhspmm is not CONFIGS["csrmhspmm"]:
+            h_prime = csrmhspmm(graph.row_indptr.int(), graph.col_indices.int(), h, attention)
+        else:
+            h_prime = MHSPMMFunction.apply(_structure(graph), None, h, attention)
+        return h_prime.view(h_prime.shape[0], -1)
+    # single head: SpMM with the attention as edge weight inside local_graph() (reference :210-214;
+    # set_weight flips the symmetric flag, so the backward takes the transpose branch)
+    edge_weight = attention.view(-1)
+    with graph.local_graph():
+        graph.edge_weight = edge_weight
+        return spmm(graph, h.squeeze(1), fast_spmm=fast_spmm)
+
+
+class MultiHeadSpMM(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.spmm = CONFIGS["fast_spmm"]
+        self.csrmhspmm = CONFIGS["csrmhspmm"]
+
+    def forward(self, graph, attention, h):
+        return mh_spmm(graph, attention, h, csrmhspmm=self.csrmhspmm, fast_spmm=self.spmm)
+
+
+def fused_gat_op(attn_row, attn_col, graph, negative_slope, in_feat, fused_gat_func=None):
+    if fused_gat_func is not None and fused_gat_func is not CONFIGS["fused_gat_func"]:
+        rp, ci = graph.row_indptr.int(), graph.col_indices.int()
+        return fused_gat_func(attn_row, attn_col, rp, ci, rp, ci, negative_slope, in_feat)
+    return FusedGATFunction.apply(attn_row, attn_col, _structure(graph), None, None, None, negative_slope, in_feat)
+
+
+class FusedGATOp(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fused_gat_func = CONFIGS["fused_gat_func"]
+
+    def forward(self, attn_row, attn_col, graph, negative_slope, in_feat):
+        return fused_gat_op(attn_row, attn_col, graph, negative_slope, in_feat, fused_gat_func=self.fused_gat_func)
