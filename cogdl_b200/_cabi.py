@@ -32,6 +32,9 @@ class HubPlanStruct(ctypes.Structure):
         ("counters", ctypes.c_void_p),
         ("partials", ctypes.c_void_p),
         ("partials_bytes", ctypes.c_int64),
+        ("seg_cost", ctypes.c_int32),
+        ("n_segs", ctypes.c_int32),
+        ("seg_starts", ctypes.c_void_p),
     ]
 
 
@@ -46,6 +49,7 @@ SIGNATURES = {
     "cogdl_b200_launch_count": (_i64, []),
     "cogdl_b200_hub_plan_count": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "cogdl_b200_hub_plan_fill": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "cogdl_b200_hub_plan_segments": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "cogdl_b200_spmm_csr_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_spmm_csr_f16": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_spmm_csr_f32_2src": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _plan_p, _vp]),
@@ -82,7 +86,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.cogdl_b200_abi_version() != 1:
+        if lib.cogdl_b200_abi_version() != 2:
             raise ImportError("libcogdl_b200.so ABI version mismatch")
         _lib = lib
     return _lib

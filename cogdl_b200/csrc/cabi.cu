@@ -70,6 +70,19 @@ __global__ void hub_fill_kernel(const int *__restrict__ rowptr, int64_t n_rows, 
   }
 }
 
+// seg_starts[k] = first row r with rowptr[r] + r >= k*Q
+__global__ void seg_starts_kernel(const int *__restrict__ rowptr, int64_t n_rows, int Q, int n_segs, int *seg_starts) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_segs; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t target = k * (int64_t)Q;
+    int64_t lo = 0, hi = n_rows;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)__ldg(rowptr + mid) + mid < target) lo = mid + 1; else hi = mid;
+    }
+    seg_starts[k] = (int)lo;
+  }
+}
+
 }  // namespace cogdl_b200
 
 using namespace cogdl_b200;
@@ -119,6 +132,16 @@ extern "C" int cogdl_b200_hub_plan_fill(const int32_t *rowptr, int64_t n_rows, i
   if (n_rows == 0) return COGDL_B200_OK;
   hub_fill_kernel<<<plan_grid(n_rows), 256, 0, s>>>(rowptr, n_rows, chunk_edges, counts_dev, hub_rows,
                                                     reinterpret_cast<int2 *>(chunks));
+  CB_LAUNCH_CHECK();
+  return COGDL_B200_OK;
+}
+
+extern "C" int cogdl_b200_hub_plan_segments(const int32_t *rowptr, int64_t n_rows, int32_t seg_cost,
+                                            int32_t n_segs, int32_t *seg_starts, cogdl_b200_stream_t stream) {
+  CB_REQUIRE(rowptr && seg_starts, "cogdl_b200_hub_plan_segments: null pointer");
+  CB_REQUIRE(n_rows >= 0 && seg_cost > 0 && n_segs >= 0, "cogdl_b200_hub_plan_segments: bad size");
+  seg_starts_kernel<<<plan_grid((int64_t)n_segs + 1), 256, 0, (cudaStream_t)stream>>>(rowptr, n_rows, seg_cost, n_segs,
+                                                                                       seg_starts);
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;
 }

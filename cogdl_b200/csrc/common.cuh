@@ -46,16 +46,22 @@ struct HubView {
   const int2 *chunks;    // (row, first_slot)
   int *counters;
   void *partials;
+  int n_segs;            // 0 => no row-stream segments
+  const int *seg_starts;
 };
 
 static inline HubView hub_view(const cogdl_b200_hub_plan_t *plan) {
-  HubView h{0, 0, nullptr, nullptr, nullptr};
+  HubView h{0, 0, nullptr, nullptr, nullptr, 0, nullptr};
   if (plan && plan->chunk_edges > 0) {
     h.chunk_edges = plan->chunk_edges;
     h.n_chunks = plan->n_chunks;
     h.chunks = reinterpret_cast<const int2 *>(plan->chunks);
     h.counters = plan->counters;
     h.partials = plan->partials;
+    if (plan->seg_starts && plan->n_segs > 0) {
+      h.n_segs = plan->n_segs;
+      h.seg_starts = plan->seg_starts;
+    }
   }
   return h;
 }
@@ -102,7 +108,9 @@ __device__ __forceinline__ void st_cg(int *p, int v) { __stcg(p, v); }
 __device__ __forceinline__ float mul_add_rn(float acc, float v, float x) {
   return __fadd_rn(acc, __fmul_rn(v, x));
 }
-__device__ __forceinline__ void mul_add_rn(float4 &acc, float v, const float4 &x) {
+// in-place forms, one per vector type
+__device__ __forceinline__ void axpy_rn(float &acc, float v, const float &x) { acc = mul_add_rn(acc, v, x); }
+__device__ __forceinline__ void axpy_rn(float4 &acc, float v, const float4 &x) {
   acc.x = mul_add_rn(acc.x, v, x.x);
   acc.y = mul_add_rn(acc.y, v, x.y);
   acc.z = mul_add_rn(acc.z, v, x.z);

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) mhspmm_kernel(const MhParams p) {
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (j + u < cnt && colok) mul_add_rn(acc, a[u], x[u]);
+        if (j + u < cnt && colok) axpy_rn(acc, a[u], x[u]);
     }
     c = cn;
     pe = pn;

@@ -14,11 +14,28 @@ import torch
 
 from . import _cabi
 
-DEFAULT_CHUNK_EDGES = 256
+import os
+
+# rows with more edges than this are cut into chunks of this many edges (hub plan)
+DEFAULT_CHUNK_EDGES = int(os.environ.get("COGDL_B200_CHUNK_EDGES", "128"))
+# rows + edges streamed by one warp of the row-stream kernels (0 disables the stream form)
+DEFAULT_SEG_COST = int(os.environ.get("COGDL_B200_SEG_COST", "128"))
+
+
+_EMPTY = {}
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """Raw device pointer of a tensor (None -> NULL).  A zero-element tensor has data_ptr() == 0;
+    the C ABI treats NULL as "argument missing", so hand it a valid dummy address instead."""
+    if t is None:
+        return None
+    if t.numel() == 0 and t.is_cuda:
+        d = _EMPTY.get(t.device)
+        if d is None:
+            d = _EMPTY[t.device] = torch.zeros(16, dtype=torch.uint8, device=t.device)
+        return ctypes.c_void_p(d.data_ptr())
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _stream(device):
@@ -47,10 +64,12 @@ def require_cuda(*tensors):
 class HubPlan:
     """Which rows are cut into edge chunks (see cogdl_b200_hub_plan_t in include/cogdl_b200.h)."""
 
-    def __init__(self, rowptr32, chunk_edges=DEFAULT_CHUNK_EDGES):
+    def __init__(self, rowptr32, chunk_edges=DEFAULT_CHUNK_EDGES, nnz=None, seg_cost=None):
         dev = rowptr32.device
         n_rows = rowptr32.numel() - 1
         self.chunk_edges = int(chunk_edges)
+        self.seg_cost = int(DEFAULT_SEG_COST if seg_cost is None else seg_cost)
+        self.n_segs, self.seg_starts = 0, None
         self.device = dev
         with torch.cuda.device(dev):
             counts = torch.empty(2, dtype=torch.int32, device=dev)
@@ -63,6 +82,11 @@ class HubPlan:
             if n_chunks > 0:
                 _cabi.call("cogdl_b200_hub_plan_fill", _ptr(rowptr32), n_rows, self.chunk_edges, _ptr(counts),
                            _ptr(self.hub_rows), _ptr(self.chunks), _stream(dev))
+            if nnz is not None and self.seg_cost > 0 and n_rows > 0:
+                self.n_segs = (int(nnz) + n_rows + self.seg_cost - 1) // self.seg_cost
+                self.seg_starts = torch.empty(self.n_segs + 1, dtype=torch.int32, device=dev)
+                _cabi.call("cogdl_b200_hub_plan_segments", _ptr(rowptr32), n_rows, self.seg_cost, self.n_segs,
+                           _ptr(self.seg_starts), _stream(dev))
 
     def struct(self, partial_bytes=0):
         """ctypes struct for one call; partial scratch comes from torch's caching allocator.
@@ -74,6 +98,8 @@ class HubPlan:
         s.hub_rows = self.hub_rows.data_ptr()
         s.chunks = self.chunks.data_ptr()
         s.counters = self.counters.data_ptr()
+        if self.seg_starts is not None:
+            s.seg_cost, s.n_segs, s.seg_starts = self.seg_cost, self.n_segs, self.seg_starts.data_ptr()
         scratch = None
         if self.n_chunks > 0 and partial_bytes > 0:
             scratch = torch.empty((partial_bytes + 15) // 16 * 4, dtype=torch.float32, device=self.device)
@@ -85,8 +111,9 @@ class HubPlan:
 class CSRStructure:
     """int32 CSR on the device + cached hub plan + cached transpose."""
 
-    def __init__(self, rowptr32, colind32, n_cols=None, chunk_edges=DEFAULT_CHUNK_EDGES):
+    def __init__(self, rowptr32, colind32, n_cols=None, chunk_edges=DEFAULT_CHUNK_EDGES, seg_cost=None):
         dev = require_cuda(rowptr32, colind32)
+        self.seg_cost = seg_cost
         if rowptr32.dtype != torch.int32 or colind32.dtype != torch.int32:
             raise ValueError("rowptr / colind must be int32 (use CSRStructure.from_int64 for Graph tensors)")
         if not (rowptr32.is_contiguous() and colind32.is_contiguous()):
@@ -121,7 +148,7 @@ class CSRStructure:
     @property
     def plan(self):
         if self._plan is None:
-            self._plan = HubPlan(self.rowptr, self.chunk_edges)
+            self._plan = HubPlan(self.rowptr, self.chunk_edges, nnz=self.nnz, seg_cost=self.seg_cost)
         return self._plan
 
     def plan_struct(self, partial_bytes=0):
@@ -143,7 +170,7 @@ class CSRStructure:
                 ws = torch.empty(max(wbytes, 16), dtype=torch.uint8, device=dev)
                 _cabi.call("cogdl_b200_csr2csc", _ptr(self.rowptr), _ptr(self.colind), self.n_rows, self.n_cols,
                            self.nnz, _ptr(colptr), _ptr(rowind), _ptr(perm), _ptr(ws), ws.numel(), _stream(dev))
-            t = CSRStructure(colptr, rowind, n_cols=self.n_rows, chunk_edges=self.chunk_edges)
+            t = CSRStructure(colptr, rowind, n_cols=self.n_rows, chunk_edges=self.chunk_edges, seg_cost=self.seg_cost)
             self._csc = (t, perm)
         return self._csc
 

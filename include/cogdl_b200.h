@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define COGDL_B200_ABI_VERSION 1
+#define COGDL_B200_ABI_VERSION 2
 
 #define COGDL_B200_OK 0
 #define COGDL_B200_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
@@ -82,6 +82,13 @@ typedef struct cogdl_b200_hub_plan {
   int32_t *counters;
   void *partials;
   int64_t partials_bytes;
+  /* Row-stream segments (optional, seg_starts == NULL => one warp per row): segment k is the run
+   * of consecutive rows [seg_starts[k], seg_starts[k+1]) whose cumulative cost rowptr[r] + r starts
+   * inside [k*seg_cost, (k+1)*seg_cost); one warp streams a segment's edges with full gather
+   * batches and flushes at row boundaries.  n_segs = ceil((nnz + n_rows) / seg_cost). */
+  int32_t seg_cost;
+  int32_t n_segs;
+  const int32_t *seg_starts; /* [n_segs + 1] */
 } cogdl_b200_hub_plan_t;
 
 /* Pass 1: counts_dev[0] = #rows with degree > chunk_edges, counts_dev[1] = #chunks.
@@ -93,6 +100,10 @@ COGDL_B200_API int cogdl_b200_hub_plan_count(const int32_t *rowptr, int64_t n_ro
 COGDL_B200_API int cogdl_b200_hub_plan_fill(const int32_t *rowptr, int64_t n_rows, int32_t chunk_edges,
                              int32_t *counts_dev, int32_t *hub_rows, int32_t *chunks,
                              cogdl_b200_stream_t stream);
+
+/* seg_starts[k] = first row r with rowptr[r] + r >= k*seg_cost, k = 0..n_segs (n_segs + 1 ints). */
+COGDL_B200_API int cogdl_b200_hub_plan_segments(const int32_t *rowptr, int64_t n_rows, int32_t seg_cost,
+                                 int32_t n_segs, int32_t *seg_starts, cogdl_b200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * CSR SpMM   Y[i,:] = sum_{p in row i} val[p] * X[colind[p],:]        (val == NULL => 1)

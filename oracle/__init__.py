@@ -87,7 +87,7 @@ def sddmm_csr(rowptr, colind, D1, D2):
 def edge_softmax_fwd(rowptr, e):
     rowptr, e = _a(rowptr, np.int32), _a(e, np.float32)
     squeeze = e.ndim == 1
-    e2 = e.reshape(e.shape[0], -1)
+    e2 = e.reshape(e.shape[0], 1 if squeeze else e.shape[1])
     out = np.zeros_like(e2)
     lib().oracle_edge_softmax_fwd_f32(_p(rowptr, _i32p), _p(e2, _f32p), _p(out, _f32p),
                                       _i64(rowptr.shape[0] - 1), _i64(e2.shape[1]))
@@ -96,7 +96,8 @@ def edge_softmax_fwd(rowptr, e):
 
 def edge_softmax_bwd(rowptr, y, g):
     rowptr, y, g = _a(rowptr, np.int32), _a(y, np.float32), _a(g, np.float32)
-    y2, g2 = y.reshape(y.shape[0], -1), g.reshape(g.shape[0], -1)
+    hh = 1 if y.ndim == 1 else y.shape[1]
+    y2, g2 = y.reshape(y.shape[0], hh), g.reshape(g.shape[0], hh)
     out = np.zeros_like(y2)
     lib().oracle_edge_softmax_bwd_f32(_p(rowptr, _i32p), _p(y2, _f32p), _p(g2, _f32p), _p(out, _f32p),
                                       _i64(rowptr.shape[0] - 1), _i64(y2.shape[1]))
@@ -126,7 +127,7 @@ def mhsddmm(rowptr, colind, grad, feat):
 
 def gather_rows(perm, x):
     perm, x = _a(perm, np.int32), _a(x, np.float32)
-    x2 = x.reshape(x.shape[0], -1)
+    x2 = x.reshape(x.shape[0], int(np.prod(x.shape[1:])) if x.ndim > 1 else 1)
     out = np.empty((perm.shape[0], x2.shape[1]), np.float32)
     lib().oracle_gather_rows_f32(_p(perm, _i32p), _p(x2, _f32p), _p(out, _f32p),
                                  _i64(perm.shape[0]), _i64(x2.shape[1]))

@@ -1,0 +1,289 @@
+"""GPU parity tests: every C-ABI op (through the Python operator layer) against the CPU oracle on
+the same seeded inputs.  Bar (north star): integer outputs bit-exact; fp32 within 1e-5 relative.
+
+`rel` below is max|a-b| / max|b| (error relative to the result's scale), the tolerance stated in
+each test.  SpMM rows that are not split by the hub plan are additionally required to be
+BIT-IDENTICAL to the oracle (= reference CPU spmm_cpu order: CSR order, separate mul and add).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.graphs import CASES, case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if b.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    import cogdl_b200  # noqa: F401
+
+    assert cogdl_b200._cabi.load().cogdl_b200_check_device() == 0, cogdl_b200._cabi.last_error()
+    return torch.device("cuda:0")
+
+
+def structure(rp, ci, n_cols, dev, chunk=256):
+    from cogdl_b200.structure import CSRStructure
+
+    return CSRStructure(torch.from_numpy(rp).to(dev), torch.from_numpy(ci).to(dev), n_cols=n_cols, chunk_edges=chunk)
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------------------------ SpMM
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("F", [128, 16, 40, 7, 256, 1, 64, 33, 300])
+@pytest.mark.parametrize("weighted", [True, False])
+def test_spmm_matches_oracle(dev, name, F, weighted):
+    from cogdl_b200.operators._raw import spmm_raw
+
+    rp, ci, n_cols = case(name)
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((n_cols, F)).astype(np.float32)
+    val = rng.random(ci.shape[0]).astype(np.float32) if weighted else None
+    ref = oracle.spmm_csr(rp, ci, val, X)
+    for chunk in (0, 256):  # 0: no hub plan -> strictly sequential -> bit exact everywhere
+        st = structure(rp, ci, n_cols, dev, chunk)
+        y = spmm_raw(st, None if val is None else T(val, dev), T(X, dev)).cpu().numpy()
+        assert y.shape == ref.shape
+        deg = np.diff(rp)
+        unsplit = deg <= chunk if chunk else np.ones_like(deg, bool)
+        assert np.array_equal(y[unsplit], ref[unsplit]), f"unsplit rows must be bit-identical (chunk={chunk})"
+        assert rel(y, ref) <= TOL
+
+
+def test_spmm_deterministic_with_hubs(dev):
+    from cogdl_b200.operators._raw import spmm_raw
+
+    rp, ci, n_cols = case("hub")
+    rng = np.random.default_rng(2)
+    X, val = T(rng.standard_normal((n_cols, 128)).astype(np.float32), dev), T(rng.random(ci.shape[0]).astype(np.float32), dev)
+    st = structure(rp, ci, n_cols, dev)
+    assert st.plan.n_hub_rows == 1 and st.plan.n_chunks == 6
+    y0 = spmm_raw(st, val, X)
+    for _ in range(5):
+        assert torch.equal(spmm_raw(st, val, X), y0)
+    assert int(st.plan.counters.abs().sum()) == 0  # arrival counters are left clean
+
+
+def test_spmm_half(dev):
+    from cogdl_b200.operators._raw import spmm_raw
+
+    rp, ci, n_cols = case("hub")
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((n_cols, 128)).astype(np.float16)
+    val = rng.random(ci.shape[0]).astype(np.float16)
+    ref = oracle.spmm_csr(rp, ci, val.astype(np.float32), X.astype(np.float32))
+    st = structure(rp, ci, n_cols, dev)
+    y = spmm_raw(st, T(val, dev), T(X, dev))
+    assert y.dtype == torch.float16
+    # fp16 storage, fp32 accumulate: error budget = one fp16 rounding of the result
+    assert rel(y.float().cpu().numpy(), ref) <= 2e-3
+
+
+def test_spmm_two_source(dev):
+    from cogdl_b200.operators._raw import spmm_2src_raw
+
+    rp, ci, n_cols = case("rect")
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((n_cols, 128)).astype(np.float32)
+    val = rng.random(ci.shape[0]).astype(np.float32)
+    ref = oracle.spmm_csr(rp, ci, val, X)
+    st = structure(rp, ci, n_cols, dev)
+    n0 = 123
+    y = spmm_2src_raw(st, T(val, dev), T(X[:n0], dev), T(X[n0:], dev)).cpu().numpy()
+    assert np.array_equal(y, ref)
+
+
+# ------------------------------------------------------------------------------------ SDDMM
+@pytest.mark.parametrize("name", ["tiny", "ragged", "hub", "rect", "empty_graph"])
+@pytest.mark.parametrize("F", [128, 16, 40, 7, 256, 1, 600])
+def test_sddmm_matches_oracle(dev, name, F):
+    from cogdl_b200.operators._raw import sddmm_raw
+
+    rp, ci, n_cols = case(name)
+    rng = np.random.default_rng(5)
+    n = rp.shape[0] - 1
+    D1 = rng.standard_normal((n, F)).astype(np.float32)
+    D2 = rng.standard_normal((n_cols, F)).astype(np.float32)
+    ref = oracle.sddmm_csr(rp, ci, D1, D2)
+    out = sddmm_raw(structure(rp, ci, n_cols, dev), T(D1, dev), T(D2, dev)).cpu().numpy()
+    assert rel(out, ref) <= TOL
+
+
+# ------------------------------------------------------------------------------------ csr2csc
+@pytest.mark.parametrize("name", list(CASES))
+def test_csr2csc_bit_exact(dev, name):
+    rp, ci, n_cols = case(name)
+    colptr, rowind, perm = oracle.csr2csc(rp, ci, n_cols)
+    st_t, p = structure(rp, ci, n_cols, dev).csc()
+    assert np.array_equal(st_t.rowptr.cpu().numpy(), colptr)
+    assert np.array_equal(st_t.colind.cpu().numpy(), rowind)
+    assert np.array_equal(p.cpu().numpy(), perm)
+
+
+def test_gather_rows(dev):
+    from cogdl_b200.operators._raw import gather_rows_raw
+
+    rng = np.random.default_rng(6)
+    perm = rng.permutation(1000).astype(np.int32)
+    x = rng.standard_normal((1000, 8)).astype(np.float32)
+    out = gather_rows_raw(T(perm, dev), T(x, dev)).cpu().numpy()
+    assert np.array_equal(out, oracle.gather_rows(perm, x))
+
+
+# ------------------------------------------------------------------------------------ edge softmax
+@pytest.mark.parametrize("name", ["tiny", "ragged", "hub", "two_hubs", "empty_graph"])
+@pytest.mark.parametrize("H", [8, 1, 2, 4, 16, 32, 3, 6])
+def test_edge_softmax_fwd_bwd(dev, name, H):
+    from cogdl_b200.operators._raw import edge_softmax_fwd_raw, edge_softmax_bwd_raw
+
+    rp, ci, n_cols = case(name)
+    rng = np.random.default_rng(7)
+    e = np.clip(rng.standard_normal((ci.shape[0], H)) * 3, -10, 10).astype(np.float32)
+    g = rng.standard_normal((ci.shape[0], H)).astype(np.float32)
+    yref = oracle.edge_softmax_fwd(rp, e)
+    gref = oracle.edge_softmax_bwd(rp, yref, g)
+    st = structure(rp, ci, n_cols, dev)
+    y = edge_softmax_fwd_raw(st, T(e, dev))
+    gin = edge_softmax_bwd_raw(st, T(yref, dev), T(g, dev))
+    assert rel(y.cpu().numpy(), yref) <= TOL
+    assert rel(gin.cpu().numpy(), gref) <= TOL
+    if ci.shape[0]:
+        # rows sum to one per head
+        seg = np.add.reduceat(y.cpu().numpy(), rp[:-1][np.diff(rp) > 0], axis=0)
+        assert np.allclose(seg, 1.0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ multi-head
+@pytest.mark.parametrize("name", ["tiny", "ragged", "hub", "rect", "empty_graph"])
+@pytest.mark.parametrize("H,F", [(8, 128), (8, 16), (8, 8), (2, 64), (4, 32), (1, 128), (3, 5), (8, 24), (2, 256)])
+def test_mhspmm_and_mhsddmm(dev, name, H, F):
+    from cogdl_b200.operators._raw import mhspmm_raw, mhsddmm_raw
+
+    rp, ci, n_cols = case(name)
+    n = rp.shape[0] - 1
+    rng = np.random.default_rng(8)
+    att = rng.random((ci.shape[0], H)).astype(np.float32)
+    feat = rng.standard_normal((n_cols, H, F)).astype(np.float32)
+    grad = rng.standard_normal((n, H, F)).astype(np.float32)
+    ref = oracle.mhspmm(rp, ci, att, feat)
+    ref_sd = oracle.mhsddmm(rp, ci, grad, feat)
+    for chunk in (0, 256):
+        st = structure(rp, ci, n_cols, dev, chunk)
+        out = mhspmm_raw(st, T(att, dev), T(feat, dev)).cpu().numpy()
+        unsplit = np.diff(rp) <= chunk if chunk else np.ones(n, bool)
+        assert np.array_equal(out[unsplit], ref[unsplit])
+        assert rel(out, ref) <= TOL
+        sd = mhsddmm_raw(st, T(grad, dev), T(feat, dev)).cpu().numpy()
+        assert rel(sd, ref_sd) <= TOL
+
+
+def test_mhspmm_transpose_with_fused_perm(dev):
+    """grad_feat of the GAT aggregation: CSC pass with att[perm] fused into the kernel."""
+    from cogdl_b200.operators._raw import mhspmm_raw
+
+    rp, ci, n_cols = case("hub")
+    rng = np.random.default_rng(9)
+    H, F = 8, 16
+    att = rng.random((ci.shape[0], H)).astype(np.float32)
+    grad = rng.standard_normal((rp.shape[0] - 1, H, F)).astype(np.float32)
+    colptr, rowind, perm = oracle.csr2csc(rp, ci, n_cols)
+    ref = oracle.mhspmm(colptr, rowind, att, grad, perm=perm)
+    st = structure(rp, ci, n_cols, dev)
+    st_t, p = st.csc()
+    out = mhspmm_raw(st_t, T(att, dev), T(grad, dev), perm=p).cpu().numpy()
+    assert rel(out, ref) <= TOL
+
+
+# ------------------------------------------------------------------------------------ scatter_max
+@pytest.mark.parametrize("name", ["tiny", "ragged", "hub", "two_hubs", "rect", "empty_graph"])
+@pytest.mark.parametrize("F", [256, 128, 16, 7, 40])
+def test_scatter_max_fwd_bwd(dev, name, F):
+    from cogdl_b200.operators._raw import scatter_max_fwd_raw, scatter_max_bwd_raw
+
+    rp, ci, n_cols = case(name)
+    n = rp.shape[0] - 1
+    rng = np.random.default_rng(10)
+    # mixed sign + deliberate ties (quantised values) to exercise "first max wins"
+    X = np.round(rng.standard_normal((n_cols, F)) * 4).astype(np.float32) / 4
+    ref, ref_id = oracle.scatter_max_fwd(rp, ci, X)
+    for chunk in (0, 256):
+        out, arg = scatter_max_fwd_raw(structure(rp, ci, n_cols, dev, chunk), T(X, dev))
+        assert np.array_equal(out.cpu().numpy(), ref)         # max is exact
+        assert np.array_equal(arg.cpu().numpy(), ref_id)      # integer output: bit exact, ties included
+    g = rng.standard_normal((n, F)).astype(np.float32)
+    gref = oracle.scatter_max_bwd(g, ref_id, n_src=n_cols)
+    gx = scatter_max_bwd_raw(T(g, dev), T(ref_id, dev), n_cols).cpu().numpy()
+    assert rel(gx, gref) <= TOL   # atomics: order differs, values within tolerance
+
+
+def test_scatter_max_reference_semantics_agree_on_positive_features(dev):
+    from cogdl_b200.operators._raw import scatter_max_fwd_raw
+
+    rp, ci, n_cols = case("ragged")
+    X = (np.random.default_rng(11).random((n_cols, 64)) + 0.01).astype(np.float32)
+    ref, ref_id = oracle.scatter_max_fwd(rp, ci, X, reference_semantics=True)
+    out, arg = scatter_max_fwd_raw(structure(rp, ci, n_cols, dev), T(X, dev))
+    has = np.diff(rp) > 0
+    assert np.array_equal(out.cpu().numpy()[has], ref[has]) and np.array_equal(arg.cpu().numpy()[has], ref_id[has])
+
+
+# ------------------------------------------------------------------------------------ fused GAT
+@pytest.mark.parametrize("name", ["tiny", "ragged", "hub", "empty_graph"])
+@pytest.mark.parametrize("H,F", [(8, 128), (8, 16), (8, 8), (1, 64), (4, 32), (3, 5), (2, 192)])
+def test_fused_gat_forward(dev, name, H, F):
+    from cogdl_b200.operators._raw import gat_fwd_raw
+
+    rp, ci, n_cols = case(name)
+    if n_cols != rp.shape[0] - 1:
+        pytest.skip("square only")
+    n = n_cols
+    rng = np.random.default_rng(12)
+    h_l = rng.standard_normal((n, H)).astype(np.float32)
+    h_r = rng.standard_normal((n, H)).astype(np.float32)
+    feat = rng.standard_normal((n, H, F)).astype(np.float32)
+    ref, ref_att = oracle.gat_fwd(rp, ci, h_l, h_r, feat, 0.2, return_att=True)
+    out, att = gat_fwd_raw(structure(rp, ci, n_cols, dev), T(h_l, dev), T(h_r, dev), T(feat, dev), 0.2, True)
+    assert rel(out.cpu().numpy(), ref) <= TOL
+    assert rel(att.cpu().numpy(), ref_att) <= TOL
+
+
+# ------------------------------------------------------------------------------------ structure tools
+def test_coo2csr_index_device_bit_exact(dev):
+    from cogdl_b200.data import coo2csr_index
+
+    rng = np.random.default_rng(13)
+    n, e = 5000, 60000
+    row = rng.integers(0, n, e).astype(np.int64)
+    rp_ref, re_ref = oracle.coo2csr_index(row, n)
+    rp, re = coo2csr_index(torch.from_numpy(row).to(dev), n)
+    assert np.array_equal(rp.cpu().numpy(), rp_ref) and np.array_equal(re.cpu().numpy(), re_ref)
+
+
+def test_errors_are_raised_not_swallowed(dev):
+    import cogdl_b200
+    from cogdl_b200.operators._raw import spmm_raw
+
+    rp, ci, n_cols = case("tiny")
+    st = structure(rp, ci, n_cols, dev)
+    with pytest.raises(ValueError):
+        spmm_raw(st, torch.ones(3, device=dev), torch.ones(n_cols, 4, device=dev))  # wrong nnz
+    with pytest.raises(RuntimeError):
+        spmm_raw(st, None, torch.ones(n_cols, 4))  # CPU tensor: no fallback
+    lib = cogdl_b200._cabi.load()
+    assert lib.cogdl_b200_spmm_csr_f32(None, None, None, None, None, 5, 4, None, None) == cogdl_b200._cabi.EINVAL
+    assert "null pointer" in cogdl_b200._cabi.last_error()
