@@ -29,7 +29,9 @@ def install(rebind_dispatch=True):
         "fused_gat_func": ops.fused_gat_func,
         "spmm_flag": True, "mh_spmm_flag": True, "fused_gat_flag": True,
     })
-    import importlib
+    import types
+
+    import cogdl.operators as ref_ops_pkg
 
     for mod_name, attrs in (
         ("cogdl.operators.spmm", {"csrspmm": ops.csrspmm}),
@@ -38,10 +40,15 @@ def install(rebind_dispatch=True):
         ("cogdl.operators.scatter_max", {"scatter_max": ops.scatter_max}),
         ("cogdl.operators.fused_gat", {"fused_gat_func": ops.fused_gat_func}),
     ):
-        try:
-            mod = importlib.import_module(mod_name)
-        except Exception:  # the reference module itself may fail to JIT-build; create the attribute anyway
-            continue
+        mod = sys.modules.get(mod_name)
+        if mod is None:
+            # Not imported yet: seed a module that already carries our operator, so a later
+            # `from cogdl.operators.scatter_max import scatter_max` (sage_layer.py:23) resolves to it
+            # and the reference's import-time JIT build of its own CUDA sources never runs.
+            mod = types.ModuleType(mod_name)
+            mod.__doc__ = "seeded by cogdl_b200.install()"
+            sys.modules[mod_name] = mod
+            setattr(ref_ops_pkg, mod_name.rsplit(".", 1)[1], mod)
         for k, v in attrs.items():
             setattr(mod, k, v)
 
