@@ -26,7 +26,7 @@ class HubPlanStruct(ctypes.Structure):
         ("chunk_edges", ctypes.c_int32),
         ("n_hub_rows", ctypes.c_int32),
         ("n_chunks", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("n_empty_rows", ctypes.c_int32),
         ("hub_rows", ctypes.c_void_p),
         ("chunks", ctypes.c_void_p),
         ("counters", ctypes.c_void_p),
@@ -34,7 +34,8 @@ class HubPlanStruct(ctypes.Structure):
         ("partials_bytes", ctypes.c_int64),
         ("seg_cost", ctypes.c_int32),
         ("n_segs", ctypes.c_int32),
-        ("seg_starts", ctypes.c_void_p),
+        ("segs", ctypes.c_void_p),
+        ("edge_row", ctypes.c_void_p),
     ]
 
 
@@ -47,9 +48,9 @@ SIGNATURES = {
     "cogdl_b200_last_error": (ctypes.c_char_p, []),
     "cogdl_b200_check_device": (ctypes.c_int, []),
     "cogdl_b200_launch_count": (_i64, []),
-    "cogdl_b200_hub_plan_count": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
-    "cogdl_b200_hub_plan_fill": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "cogdl_b200_hub_plan_segments": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "cogdl_b200_hub_plan_count": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "cogdl_b200_hub_plan_fill": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cogdl_b200_edge_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "cogdl_b200_spmm_csr_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_spmm_csr_f16": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_spmm_csr_f32_2src": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _plan_p, _vp]),
@@ -86,7 +87,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.cogdl_b200_abi_version() != 2:
+        if lib.cogdl_b200_abi_version() != 3:
             raise ImportError("libcogdl_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -34,9 +34,20 @@ int check_plan(const cogdl_b200_hub_plan_t *plan, int64_t need_partial_bytes) {
   return COGDL_B200_OK;
 }
 
-// counts[0] += #hub rows, counts[1] += #chunks
-__global__ void hub_count_kernel(const int *__restrict__ rowptr, int64_t n_rows, int T, int *counts) {
-  int hubs = 0, chunks = 0;
+// A row starts a segment iff it is not a hub and (it is row 0, or the previous row is a hub, or the
+// cumulative cost P(r) = rowptr[r] + r crosses a multiple of Q between r-1 and r).
+__device__ __forceinline__ bool seg_start(const int *rowptr, int64_t r, int T, int Q) {
+  const int b = rowptr[r], e = rowptr[r + 1];
+  if (e - b > T) return false;
+  if (r == 0) return true;
+  const int pb = rowptr[r - 1];
+  if (b - pb > T) return true;
+  return ((int64_t)b + r) / Q != ((int64_t)pb + r - 1) / Q;
+}
+
+// counts[0] += #hub rows, [1] += #chunks, [2] += #empty rows, [3] += #segments
+__global__ void hub_count_kernel(const int *__restrict__ rowptr, int64_t n_rows, int T, int Q, int *counts) {
+  int hubs = 0, chunks = 0, empties = 0, segs = 0;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
        r += (int64_t)gridDim.x * blockDim.x) {
     const int deg = rowptr[r + 1] - rowptr[r];
@@ -44,19 +55,24 @@ __global__ void hub_count_kernel(const int *__restrict__ rowptr, int64_t n_rows,
       hubs += 1;
       chunks += (deg + T - 1) / T;
     }
+    if (deg == 0) empties += 1;
+    if (Q > 0 && seg_start(rowptr, r, T, Q)) segs += 1;
   }
   for (int s = 16; s > 0; s >>= 1) {
     hubs += __shfl_xor_sync(FULL, hubs, s);
     chunks += __shfl_xor_sync(FULL, chunks, s);
+    empties += __shfl_xor_sync(FULL, empties, s);
+    segs += __shfl_xor_sync(FULL, segs, s);
   }
-  if ((threadIdx.x & 31) == 0 && hubs) {
-    atomicAdd(counts + 0, hubs);
-    atomicAdd(counts + 1, chunks);
+  if ((threadIdx.x & 31) == 0) {
+    if (hubs) { atomicAdd(counts + 0, hubs); atomicAdd(counts + 1, chunks); }
+    if (empties) atomicAdd(counts + 2, empties);
+    if (segs) atomicAdd(counts + 3, segs);
   }
 }
 
-__global__ void hub_fill_kernel(const int *__restrict__ rowptr, int64_t n_rows, int T, int *counts,
-                                int *hub_rows, int2 *chunks) {
+__global__ void hub_fill_kernel(const int *__restrict__ rowptr, int64_t n_rows, int T, int Q, int *counts,
+                                int *hub_rows, int2 *chunks, int2 *segs) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
        r += (int64_t)gridDim.x * blockDim.x) {
     const int deg = rowptr[r + 1] - rowptr[r];
@@ -67,19 +83,27 @@ __global__ void hub_fill_kernel(const int *__restrict__ rowptr, int64_t n_rows, 
       hub_rows[h] = (int)r;
       for (int j = 0; j < n; ++j) chunks[first + j] = make_int2((int)r, first);
     }
+    if (Q > 0 && segs && seg_start(rowptr, r, T, Q)) {
+      int64_t end = r + 1;   // extend to the next hub row / segment start (at most Q rows away)
+      while (end < n_rows && (rowptr[end + 1] - rowptr[end]) <= T &&
+             ((int64_t)rowptr[end] + end) / Q == ((int64_t)rowptr[end - 1] + end - 1) / Q)
+        ++end;
+      const int k = atomicAdd(counts + 3, 1);
+      segs[k] = make_int2((int)r, (int)end);
+    }
   }
 }
 
-// seg_starts[k] = first row r with rowptr[r] + r >= k*Q
-__global__ void seg_starts_kernel(const int *__restrict__ rowptr, int64_t n_rows, int Q, int n_segs, int *seg_starts) {
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_segs; k += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t target = k * (int64_t)Q;
+// edge_row[p] = largest r with rowptr[r] <= p
+__global__ void edge_rows_kernel(const int *__restrict__ rowptr, int64_t n_rows, int64_t nnz, int *edge_row) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
     int64_t lo = 0, hi = n_rows;
     while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if ((int64_t)__ldg(rowptr + mid) + mid < target) lo = mid + 1; else hi = mid;
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (__ldg(rowptr + mid) <= p) lo = mid; else hi = mid - 1;
     }
-    seg_starts[k] = (int)lo;
+    edge_row[p] = (int)lo;
   }
 }
 
@@ -111,37 +135,40 @@ static int plan_grid(int64_t n_rows) {
 }
 
 extern "C" int cogdl_b200_hub_plan_count(const int32_t *rowptr, int64_t n_rows, int32_t chunk_edges,
-                                         int32_t *counts_dev, cogdl_b200_stream_t stream) {
+                                         int32_t seg_cost, int32_t *counts_dev, cogdl_b200_stream_t stream) {
   CB_REQUIRE(rowptr && counts_dev, "cogdl_b200_hub_plan_count: null pointer");
   CB_REQUIRE(n_rows >= 0 && chunk_edges > 0, "cogdl_b200_hub_plan_count: bad size");
   cudaStream_t s = (cudaStream_t)stream;
-  CB_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int32_t), s));
+  CB_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), s));
   if (n_rows == 0) return COGDL_B200_OK;
-  hub_count_kernel<<<plan_grid(n_rows), 256, 0, s>>>(rowptr, n_rows, chunk_edges, counts_dev);
+  hub_count_kernel<<<plan_grid(n_rows), 256, 0, s>>>(rowptr, n_rows, chunk_edges, seg_cost, counts_dev);
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;
 }
 
 extern "C" int cogdl_b200_hub_plan_fill(const int32_t *rowptr, int64_t n_rows, int32_t chunk_edges,
-                                        int32_t *counts_dev, int32_t *hub_rows, int32_t *chunks,
-                                        cogdl_b200_stream_t stream) {
+                                        int32_t seg_cost, int32_t *counts_dev, int32_t *hub_rows,
+                                        int32_t *chunks, int32_t *segs, cogdl_b200_stream_t stream) {
   CB_REQUIRE(rowptr && counts_dev && hub_rows && chunks, "cogdl_b200_hub_plan_fill: null pointer");
   CB_REQUIRE(n_rows >= 0 && chunk_edges > 0, "cogdl_b200_hub_plan_fill: bad size");
+  CB_REQUIRE(seg_cost <= 0 || segs, "cogdl_b200_hub_plan_fill: segs is null but seg_cost > 0");
   cudaStream_t s = (cudaStream_t)stream;
-  CB_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int32_t), s));
+  CB_CUDA(cudaMemsetAsync(counts_dev, 0, 4 * sizeof(int32_t), s));
   if (n_rows == 0) return COGDL_B200_OK;
-  hub_fill_kernel<<<plan_grid(n_rows), 256, 0, s>>>(rowptr, n_rows, chunk_edges, counts_dev, hub_rows,
-                                                    reinterpret_cast<int2 *>(chunks));
+  hub_fill_kernel<<<plan_grid(n_rows), 256, 0, s>>>(rowptr, n_rows, chunk_edges, seg_cost, counts_dev, hub_rows,
+                                                    reinterpret_cast<int2 *>(chunks), reinterpret_cast<int2 *>(segs));
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;
 }
 
-extern "C" int cogdl_b200_hub_plan_segments(const int32_t *rowptr, int64_t n_rows, int32_t seg_cost,
-                                            int32_t n_segs, int32_t *seg_starts, cogdl_b200_stream_t stream) {
-  CB_REQUIRE(rowptr && seg_starts, "cogdl_b200_hub_plan_segments: null pointer");
-  CB_REQUIRE(n_rows >= 0 && seg_cost > 0 && n_segs >= 0, "cogdl_b200_hub_plan_segments: bad size");
-  seg_starts_kernel<<<plan_grid((int64_t)n_segs + 1), 256, 0, (cudaStream_t)stream>>>(rowptr, n_rows, seg_cost, n_segs,
-                                                                                       seg_starts);
+extern "C" int cogdl_b200_edge_rows(const int32_t *rowptr, int64_t n_rows, int64_t nnz, int32_t *edge_row,
+                                    cogdl_b200_stream_t stream) {
+  CB_REQUIRE(n_rows >= 0 && nnz >= 0, "cogdl_b200_edge_rows: negative size");
+  if (nnz == 0) return COGDL_B200_OK;
+  CB_REQUIRE(rowptr && edge_row, "cogdl_b200_edge_rows: null pointer");
+  int64_t blocks = ceil_div(nnz, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  edge_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rowptr, n_rows, nnz, edge_row);
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;
 }

@@ -47,20 +47,24 @@ struct HubView {
   int *counters;
   void *partials;
   int n_segs;            // 0 => no row-stream segments
-  const int *seg_starts;
+  const int2 *segs;      // (row_begin, row_end), hub-free
+  const int *edge_row;
+  int n_empty_rows;
 };
 
 static inline HubView hub_view(const cogdl_b200_hub_plan_t *plan) {
-  HubView h{0, 0, nullptr, nullptr, nullptr, 0, nullptr};
+  HubView h{0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0};
   if (plan && plan->chunk_edges > 0) {
     h.chunk_edges = plan->chunk_edges;
     h.n_chunks = plan->n_chunks;
     h.chunks = reinterpret_cast<const int2 *>(plan->chunks);
     h.counters = plan->counters;
     h.partials = plan->partials;
-    if (plan->seg_starts && plan->n_segs > 0) {
+    if (plan->segs && plan->edge_row && plan->n_segs > 0) {
       h.n_segs = plan->n_segs;
-      h.seg_starts = plan->seg_starts;
+      h.segs = reinterpret_cast<const int2 *>(plan->segs);
+      h.edge_row = plan->edge_row;
+      h.n_empty_rows = plan->n_empty_rows;
     }
   }
   return h;
@@ -88,6 +92,25 @@ __device__ __forceinline__ float ld_stream(const float *p) {
 // Gathered feature rows: read-only path, default caching (hub columns do get reused).
 __device__ __forceinline__ float4 ld_gather(const float4 *p) { return __ldg(p); }
 __device__ __forceinline__ float ld_gather(const float *p) { return __ldg(p); }
+
+// L2 eviction-priority hints (createpolicy + ld/st .L2::cache_hint): the gathered matrix X is the
+// only data with reuse, everything else is touched once.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_gather_hint(const float4 *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_gather_hint(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
 
 // Output rows are written once and never re-read by the kernel: streaming store.
 __device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }

@@ -25,7 +25,7 @@ struct EsParams {
   float *out;
   int64_t n_rows;
   int H;
-  int hub_T;              // rows with degree > hub_T are left to the hub kernel (0: none)
+  int hub_T;              // plan chunk size: rows above it are listed in hub_rows (0: no plan)
   const int *hub_rows;
   int n_hub_rows;
 };
@@ -40,6 +40,9 @@ __device__ __forceinline__ float head_sum(float v, int H) {
   return v;
 }
 
+// Rows with more elements (deg * H) than this go to the block-per-row kernel when a plan lists them.
+constexpr int64_t BLOCK_ROW_ELEMS = 4096;
+
 // ---------------------------------------------------------------- warp per row, H = 2^k <= 32
 template <bool BWD>
 __global__ void __launch_bounds__(256) es_warp_kernel(const EsParams p) {
@@ -49,8 +52,9 @@ __global__ void __launch_bounds__(256) es_warp_kernel(const EsParams p) {
   if (row >= p.n_rows) return;  // whole warp
   const int lb = __ldg(p.rowptr + row), hb = __ldg(p.rowptr + row + 1);
   const int deg = hb - lb;
-  if (deg == 0 || (p.hub_T > 0 && deg > p.hub_T)) return;
   const int64_t n = (int64_t)deg * p.H;
+  // rows with more than BLOCK_ROW_ELEMS elements are listed hub rows: a whole block takes them
+  if (deg == 0 || (p.hub_T > 0 && deg > p.hub_T && n > BLOCK_ROW_ELEMS)) return;
   const float *a = p.a + (int64_t)lb * p.H;
   const float *b = BWD ? p.b + (int64_t)lb * p.H : nullptr;
   float *o = p.out + (int64_t)lb * p.H;
@@ -89,60 +93,119 @@ __global__ void __launch_bounds__(256) es_warp_kernel(const EsParams p) {
     }
     return;
   }
-  // long row: 3 passes (2 for bwd); re-reads hit L1/L2
+  // long row: 3 passes (2 for bwd), 4 independent loads in flight per lane; re-reads hit L1/L2
   if (!BWD) {
-    float m = -CUDART_INF_F;
-    for (int64_t t = lane; t < n; t += 32) m = fmaxf(m, __ldg(a + t));
-    m = head_max(m, p.H);
-    float s = 0.f;
-    for (int64_t t = lane; t < n; t += 32) s += expf(__ldg(a + t) - m);
-    s = head_sum(s, p.H);
-    for (int64_t t = lane; t < n; t += 32) st_stream(o + t, expf(__ldg(a + t) - m) / s);
+    float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
+    int64_t t = lane;
+    for (; t + 96 < n; t += 128) {
+      const float x0 = __ldg(a + t), x1 = __ldg(a + t + 32), x2 = __ldg(a + t + 64), x3 = __ldg(a + t + 96);
+      m0 = fmaxf(m0, x0); m1 = fmaxf(m1, x1); m2 = fmaxf(m2, x2); m3 = fmaxf(m3, x3);
+    }
+    for (; t < n; t += 32) m0 = fmaxf(m0, __ldg(a + t));
+    const float m = head_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), p.H);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    t = lane;
+    for (; t + 96 < n; t += 128) {
+      const float x0 = __ldg(a + t), x1 = __ldg(a + t + 32), x2 = __ldg(a + t + 64), x3 = __ldg(a + t + 96);
+      s0 += expf(x0 - m); s1 += expf(x1 - m); s2 += expf(x2 - m); s3 += expf(x3 - m);
+    }
+    for (; t < n; t += 32) s0 += expf(__ldg(a + t) - m);
+    const float s = head_sum((s0 + s1) + (s2 + s3), p.H);
+    t = lane;
+    for (; t + 96 < n; t += 128) {
+      const float x0 = __ldg(a + t), x1 = __ldg(a + t + 32), x2 = __ldg(a + t + 64), x3 = __ldg(a + t + 96);
+      st_stream(o + t, expf(x0 - m) / s); st_stream(o + t + 32, expf(x1 - m) / s);
+      st_stream(o + t + 64, expf(x2 - m) / s); st_stream(o + t + 96, expf(x3 - m) / s);
+    }
+    for (; t < n; t += 32) st_stream(o + t, expf(__ldg(a + t) - m) / s);
   } else {
-    float s = 0.f;
-    for (int64_t t = lane; t < n; t += 32) s = fmaf(__ldg(a + t), __ldg(b + t), s);
-    s = head_sum(s, p.H);
-    for (int64_t t = lane; t < n; t += 32) st_stream(o + t, __ldg(a + t) * (__ldg(b + t) - s));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t t = lane;
+    for (; t + 96 < n; t += 128) {
+      s0 = fmaf(__ldg(a + t), __ldg(b + t), s0); s1 = fmaf(__ldg(a + t + 32), __ldg(b + t + 32), s1);
+      s2 = fmaf(__ldg(a + t + 64), __ldg(b + t + 64), s2); s3 = fmaf(__ldg(a + t + 96), __ldg(b + t + 96), s3);
+    }
+    for (; t < n; t += 32) s0 = fmaf(__ldg(a + t), __ldg(b + t), s0);
+    const float s = head_sum((s0 + s1) + (s2 + s3), p.H);
+    t = lane;
+    for (; t + 96 < n; t += 128) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_stream(o + t + 32 * q, __ldg(a + t + 32 * q) * (__ldg(b + t + 32 * q) - s));
+    }
+    for (; t < n; t += 32) st_stream(o + t, __ldg(a + t) * (__ldg(b + t) - s));
   }
 }
 
 // ---------------------------------------------------------------- block per hub row, H = 2^k <= 32
+// 1024 threads per hub row; every pass keeps 4 independent loads in flight per thread (the hub of an
+// arxiv-shaped graph is 22 K edges x 8 heads = 724 KB: latency-bound unless the loads are batched).
+constexpr int HUB_THREADS = 1024;
+constexpr int HUB_WARPS = HUB_THREADS / 32;
+
 template <bool MAX>
-__device__ __forceinline__ float block_head_reduce(float v, int H, float *smem /*[8][32]*/) {
+__device__ __forceinline__ float block_head_reduce(float v, int H, float *smem /*[HUB_WARPS][32]*/) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   v = MAX ? head_max(v, H) : head_sum(v, H);
   __syncthreads();  // smem reuse between successive reductions
   smem[wid * 32 + lane] = v;
   __syncthreads();
   float r = smem[lane];
-#pragma unroll
-  for (int q = 1; q < 8; ++q) r = MAX ? fmaxf(r, smem[q * 32 + lane]) : r + smem[q * 32 + lane];
+#pragma unroll 8
+  for (int q = 1; q < HUB_WARPS; ++q) r = MAX ? fmaxf(r, smem[q * 32 + lane]) : r + smem[q * 32 + lane];
   return r;  // every thread: result for its own head (lane % H)
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(256) es_hub_kernel(const EsParams p) {
-  __shared__ float smem[8 * 32];
+__global__ void __launch_bounds__(HUB_THREADS) es_hub_kernel(const EsParams p) {
+  __shared__ float smem[HUB_WARPS * 32];
   const int row = __ldg(p.hub_rows + blockIdx.x);
   const int lb = __ldg(p.rowptr + row), hb = __ldg(p.rowptr + row + 1);
   const int64_t n = (int64_t)(hb - lb) * p.H;
+  if (n <= BLOCK_ROW_ELEMS) return;   // small listed rows stay with the warp kernel (block-uniform)
   const float *a = p.a + (int64_t)lb * p.H;
   const float *b = BWD ? p.b + (int64_t)lb * p.H : nullptr;
   float *o = p.out + (int64_t)lb * p.H;
-  const int tid = threadIdx.x;  // 256 % H == 0 => head = tid % H is loop-invariant
+  const int tid = threadIdx.x;  // HUB_THREADS % H == 0 => head = tid % H is loop-invariant
+  constexpr int ST = HUB_THREADS;
   if (!BWD) {
-    float m = -CUDART_INF_F;
-    for (int64_t t = tid; t < n; t += 256) m = fmaxf(m, __ldg(a + t));
-    m = block_head_reduce<true>(m, p.H, smem);
-    float s = 0.f;
-    for (int64_t t = tid; t < n; t += 256) s += expf(__ldg(a + t) - m);
-    s = block_head_reduce<false>(s, p.H, smem);
-    for (int64_t t = tid; t < n; t += 256) st_stream(o + t, expf(__ldg(a + t) - m) / s);
+    float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
+    int64_t t = tid;
+    for (; t + 3 * ST < n; t += 4 * ST) {
+      const float x0 = __ldg(a + t), x1 = __ldg(a + t + ST), x2 = __ldg(a + t + 2 * ST), x3 = __ldg(a + t + 3 * ST);
+      m0 = fmaxf(m0, x0); m1 = fmaxf(m1, x1); m2 = fmaxf(m2, x2); m3 = fmaxf(m3, x3);
+    }
+    for (; t < n; t += ST) m0 = fmaxf(m0, __ldg(a + t));
+    const float m = block_head_reduce<true>(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), p.H, smem);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    t = tid;
+    for (; t + 3 * ST < n; t += 4 * ST) {
+      const float x0 = __ldg(a + t), x1 = __ldg(a + t + ST), x2 = __ldg(a + t + 2 * ST), x3 = __ldg(a + t + 3 * ST);
+      s0 += expf(x0 - m); s1 += expf(x1 - m); s2 += expf(x2 - m); s3 += expf(x3 - m);
+    }
+    for (; t < n; t += ST) s0 += expf(__ldg(a + t) - m);
+    const float s = block_head_reduce<false>((s0 + s1) + (s2 + s3), p.H, smem);
+    t = tid;
+    for (; t + 3 * ST < n; t += 4 * ST) {
+      const float x0 = __ldg(a + t), x1 = __ldg(a + t + ST), x2 = __ldg(a + t + 2 * ST), x3 = __ldg(a + t + 3 * ST);
+      st_stream(o + t, expf(x0 - m) / s); st_stream(o + t + ST, expf(x1 - m) / s);
+      st_stream(o + t + 2 * ST, expf(x2 - m) / s); st_stream(o + t + 3 * ST, expf(x3 - m) / s);
+    }
+    for (; t < n; t += ST) st_stream(o + t, expf(__ldg(a + t) - m) / s);
   } else {
-    float s = 0.f;
-    for (int64_t t = tid; t < n; t += 256) s = fmaf(__ldg(a + t), __ldg(b + t), s);
-    s = block_head_reduce<false>(s, p.H, smem);
-    for (int64_t t = tid; t < n; t += 256) st_stream(o + t, __ldg(a + t) * (__ldg(b + t) - s));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t t = tid;
+    for (; t + 3 * ST < n; t += 4 * ST) {
+      s0 = fmaf(__ldg(a + t), __ldg(b + t), s0); s1 = fmaf(__ldg(a + t + ST), __ldg(b + t + ST), s1);
+      s2 = fmaf(__ldg(a + t + 2 * ST), __ldg(b + t + 2 * ST), s2); s3 = fmaf(__ldg(a + t + 3 * ST), __ldg(b + t + 3 * ST), s3);
+    }
+    for (; t < n; t += ST) s0 = fmaf(__ldg(a + t), __ldg(b + t), s0);
+    const float s = block_head_reduce<false>((s0 + s1) + (s2 + s3), p.H, smem);
+    t = tid;
+    for (; t + 3 * ST < n; t += 4 * ST) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_stream(o + t + q * ST, __ldg(a + t + q * ST) * (__ldg(b + t + q * ST) - s));
+    }
+    for (; t < n; t += ST) st_stream(o + t, __ldg(a + t) * (__ldg(b + t) - s));
   }
 }
 
@@ -200,7 +263,7 @@ static int es_entry(const int32_t *rowptr, const float *a, const float *b, float
   }
   if (plan && plan->chunk_edges > 0 && plan->n_hub_rows > 0) {
     p.hub_T = plan->chunk_edges; p.hub_rows = plan->hub_rows; p.n_hub_rows = plan->n_hub_rows;
-    es_hub_kernel<BWD><<<(unsigned)p.n_hub_rows, 256, 0, s>>>(p);  // long rows first
+    es_hub_kernel<BWD><<<(unsigned)p.n_hub_rows, HUB_THREADS, 0, s>>>(p);  // long rows first
     CB_LAUNCH_CHECK();
   }
   es_warp_kernel<BWD><<<(unsigned)blocks, 256, 0, s>>>(p);

@@ -15,6 +15,7 @@
 // order and rounding are those of the SpMM (CSR order, separate fp32 mul and add), i.e. the
 // reference's CPU fallback (one spmm_cpu per head, spmm_utils.py:216-225).
 #include "common.cuh"
+#include "stream.cuh"
 
 namespace cogdl_b200 {
 
@@ -148,6 +149,15 @@ static int dispatch_mh(MhParams &p, cudaStream_t s) {
   int g = 1;
   while (g < 32 && g < n) g <<= 1;
   p.S = (int)ceil_div(n, g);
+  if (g == 32 && p.hub.n_segs > 0) {
+    // row-stream form: one warp per (segment or hub chunk, 512-byte slice)
+    StreamParams q;
+    q.rowptr = p.rowptr; q.colind = p.colind; q.val = nullptr; q.att = p.att; q.perm = p.perm;
+    q.X0 = p.feat; q.X1 = p.feat; q.n0 = INT64_MAX; q.Y = p.out; q.ldv = p.HFV; q.H = p.H; q.FVL = p.FVL;
+    q.S = p.S; q.hub = p.hub;
+    if (p.n_rows == 0) q.hub.n_segs = 0;   // chunks-only call (fused GAT hub path)
+    return launch_stream<VecT, 1, 8, 3>(q, MODE_MULTIHEAD, s);
+  }
   switch (g) {
     case 1: return launch_mh<VecT, 1>(p, s);
     case 2: return launch_mh<VecT, 2>(p, s);

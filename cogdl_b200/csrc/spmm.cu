@@ -24,6 +24,7 @@
 //     unsplit rows are bit-identical to the reference CPU SpMM (spmm_cpu.cpp:24-36);
 //   * 64-bit row offsets (the reference's `int offset = colInd * k` overflows at N*F >= 2^31).
 #include "common.cuh"
+#include "stream.cuh"
 
 #include <cuda_fp16.h>
 
@@ -161,223 +162,49 @@ __global__ void __launch_bounds__(256) spmm_kernel(const SpmmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Row-stream kernel (used when the plan carries segments; full-warp groups only).
-//
-// One warp owns a cost-balanced run of consecutive rows (a segment, ~seg_cost rows+edges) and
-// streams their edges, which are contiguous in colind/val: a 32-edge index slab is loaded with
-// one coalesced request and typically spans several short rows; the U-deep gather batches are
-// therefore always full (the row-per-warp form issues only deg gathers per short row behind a
-// rowptr -> colind -> X dependent chain).  Accumulation stays strictly in CSR order per row;
-// when the running edge index reaches the current row's end the accumulator is flushed to Y
-// (warp-uniform branch).  Row ends for the next 32 rows live one per lane (rowptr window) and
-// are fetched by shuffle.  Hub rows (degree > chunk) met in the stream are skipped: the chunk
-// items at the front of the grid own them.
+// Row-stream form (stream.cuh), used whenever the plan carries segments and a full warp owns the
+// row (F >= 68, or >= 17 on the scalar path).  COGDL_B200_SPMM_VARIANT (experiments only) picks
+// the unroll depth / occupancy target of the F <= 128 instantiation; the default is the variant
+// measured fastest on B200 (profiles/).
 // ------------------------------------------------------------------------------------------
-template <typename VecT, int NV, bool HAS_VAL, int U, bool TWO_SRC, int MINB>
-__global__ void __launch_bounds__(256, MINB) spmm_stream_kernel(const SpmmParams p) {
-  constexpr int TILE = 32 * NV;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const VecT *X0 = reinterpret_cast<const VecT *>(p.X0);
-  const VecT *X1 = reinterpret_cast<const VecT *>(p.X1);
-  VecT *Y = reinterpret_cast<VecT *>(p.Y);
-  VecT *P = reinterpret_cast<VecT *>(p.hub.partials);
-  const int T = p.hub.chunk_edges;
-
-  if (warp < p.hub.n_chunks) {
-    // ---------------- hub chunk: one row's edge range [lb, hb), partial sum -> scratch
-    const WorkItem w = decode_item(warp, 0, p.rowptr, p.hub);
-    for (int tile0 = 0; tile0 < p.FV; tile0 += TILE) {
-      const int cv = tile0 + lane;
-      bool colok[NV];
-      VecT acc[NV];
-#pragma unroll
-      for (int k = 0; k < NV; ++k) { colok[k] = (cv + k * 32) < p.FV; acc[k] = vzero<VecT>(); }
-      int c = 0;
-      float v = 0.f;
-      if (w.lb + lane < w.hb) { c = ld_stream(p.colind + w.lb + lane); v = HAS_VAL ? ld_stream(p.val + w.lb + lane) : 1.f; }
-      for (int e = w.lb; e < w.hb; e += 32) {
-        const int cnt = min(32, w.hb - e);
-        int cn = 0;
-        float vn = 0.f;
-        if (e + 32 + lane < w.hb) { cn = ld_stream(p.colind + e + 32 + lane); vn = HAS_VAL ? ld_stream(p.val + e + 32 + lane) : 1.f; }
-#pragma unroll 1
-        for (int j = 0; j < cnt; j += U) {
-          VecT x[U][NV];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int cj = __shfl_sync(FULL, c, j + u);
-            if (j + u < cnt) {
-              const VecT *xp = (!TWO_SRC || cj < p.n0) ? X0 + (int64_t)cj * p.FV : X1 + ((int64_t)cj - p.n0) * p.FV;
-#pragma unroll
-              for (int k = 0; k < NV; ++k)
-                if (colok[k]) x[u][k] = ld_gather(xp + cv + k * 32);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const float vj = __shfl_sync(FULL, v, j + u);
-            if (j + u < cnt) {
-#pragma unroll
-              for (int k = 0; k < NV; ++k)
-                if (colok[k]) axpy_rn(acc[k], vj, x[u][k]);
-            }
-          }
-        }
-        c = cn;
-        v = vn;
-      }
-#pragma unroll
-      for (int k = 0; k < NV; ++k)
-        if (colok[k]) st_cg(P + (int64_t)w.slot * p.FV + cv + k * 32, acc[k]);
-    }
-    if (hub_arrive_last<32>(w, p.hub, lane)) {
-      for (int cv = lane; cv < p.FV; cv += 32) {
-        const VecT *pp = P + (int64_t)w.first * p.FV + cv;
-        VecT s = ld_cg(pp);
-        for (int q = 1; q < w.n_row_chunks; ++q) add_rn(s, ld_cg(pp + (int64_t)q * p.FV));
-        st_stream(Y + (int64_t)w.row * p.FV + cv, s);
-      }
-    }
-    return;
-  }
-
-  // ---------------- stream segment
-  const int64_t seg = warp - p.hub.n_chunks;
-  if (seg >= p.hub.n_segs) return;
-  const int r_begin = __ldg(p.hub.seg_starts + seg);
-  const int r_end = __ldg(p.hub.seg_starts + seg + 1);
-  if (r_begin >= r_end) return;
-
-  for (int tile0 = 0; tile0 < p.FV; tile0 += TILE) {
-    const int cv = tile0 + lane;
-    bool colok[NV];
-    VecT acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) { colok[k] = (cv + k * 32) < p.FV; acc[k] = vzero<VecT>(); }
-
-    int r = r_begin;
-    int e = __ldg(p.rowptr + r);
-    int rwin = r;          // first row of the rowptr window
-    int rp_end = 0;        // lane l: end edge of row rwin + l
-    unsigned hubmask = 0;  // bit l: row rwin + l is a hub row
-    auto load_window = [&]() {
-      const int row = rwin + lane;
-      int b = 0, en = 0;
-      const bool ok = row < r_end;
-      if (ok) { b = __ldg(p.rowptr + row); en = __ldg(p.rowptr + row + 1); }
-      rp_end = ok ? en : 0x7fffffff;
-      hubmask = __ballot_sync(FULL, ok && T > 0 && (en - b) > T);
-    };
-    load_window();
-    int re = __shfl_sync(FULL, rp_end, 0);
-
-    while (true) {
-      // (A) retire rows that are complete at edge e (incl. empty rows); skip hub rows
-      while (r < r_end) {
-        const bool hub = (hubmask >> (r - rwin)) & 1u;
-        if (hub) {
-          e = re;
-        } else if (re == e) {
-#pragma unroll
-          for (int k = 0; k < NV; ++k)
-            if (colok[k]) { st_stream(Y + (int64_t)r * p.FV + cv + k * 32, acc[k]); acc[k] = vzero<VecT>(); }
-        } else {
-          break;
-        }
-        ++r;
-        if (r - rwin == 32) { rwin = r; load_window(); }
-        re = __shfl_sync(FULL, rp_end, r - rwin);
-      }
-      if (r >= r_end) break;
-      // (B) next index slab: up to 32 edges, never into a hub row and never past the window
-      const unsigned hm = hubmask >> (r - rwin);
-      const int last = min(31, r_end - 1 - rwin);
-      const int lim_row = hm ? (r - rwin) + __ffs(hm) - 1 : last + 1;  // first hub row of the window (or one past its last row)
-      const int lim_e = __shfl_sync(FULL, rp_end, lim_row - 1);
-      const int cnt = min(32, lim_e - e);
-      int c = 0;
-      float v = 0.f;
-      if (lane < cnt) { c = ld_stream(p.colind + e + lane); v = HAS_VAL ? ld_stream(p.val + e + lane) : 1.f; }
-      // (C) full gather batches; flush at row ends
-#pragma unroll 1
-      for (int j = 0; j < cnt; j += U) {
-        VecT x[U][NV];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int cj = __shfl_sync(FULL, c, j + u);
-          if (j + u < cnt) {
-            const VecT *xp = (!TWO_SRC || cj < p.n0) ? X0 + (int64_t)cj * p.FV : X1 + ((int64_t)cj - p.n0) * p.FV;
-#pragma unroll
-            for (int k = 0; k < NV; ++k)
-              if (colok[k]) x[u][k] = ld_gather(xp + cv + k * 32);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float vj = __shfl_sync(FULL, v, j + u);
-          if (j + u < cnt) {
-            while (re == e + j + u) {   // rows ending before this edge (warp-uniform)
-#pragma unroll
-              for (int k = 0; k < NV; ++k)
-                if (colok[k]) { st_stream(Y + (int64_t)r * p.FV + cv + k * 32, acc[k]); acc[k] = vzero<VecT>(); }
-              ++r;
-              re = __shfl_sync(FULL, rp_end, r - rwin);
-            }
-#pragma unroll
-            for (int k = 0; k < NV; ++k)
-              if (colok[k]) axpy_rn(acc[k], vj, x[u][k]);
-          }
-        }
-      }
-      e += cnt;
-    }
-  }
-}
-
-// Tuning knob (experiments only): COGDL_B200_SPMM_VARIANT picks the unroll depth / occupancy
-// target of the F<=128 row-stream kernel.  The default is the variant measured fastest on B200.
 static int spmm_variant() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("COGDL_B200_SPMM_VARIANT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 7;
   }
   return v;
 }
 
-template <typename VecT, int NV, int U, int MINB>
-static int launch_spmm_stream_v(const SpmmParams &p, cudaStream_t stream) {
-  const int64_t warps = (int64_t)p.hub.n_chunks + p.hub.n_segs;
-  const int64_t blocks = ceil_div(warps * 32, 256);
-  if (blocks == 0) return COGDL_B200_OK;
-  if (blocks > 0x7fffffffLL)
-    return set_error(COGDL_B200_EINVAL, "spmm: problem too large for one launch (blocks=%lld)", (long long)blocks);
-  const bool two = p.n0 != INT64_MAX;
-  if (p.val) {
-    if (two) spmm_stream_kernel<VecT, NV, true, U, true, MINB><<<(unsigned)blocks, 256, 0, stream>>>(p);
-    else spmm_stream_kernel<VecT, NV, true, U, false, MINB><<<(unsigned)blocks, 256, 0, stream>>>(p);
-  } else {
-    if (two) spmm_stream_kernel<VecT, NV, false, U, true, MINB><<<(unsigned)blocks, 256, 0, stream>>>(p);
-    else spmm_stream_kernel<VecT, NV, false, U, false, MINB><<<(unsigned)blocks, 256, 0, stream>>>(p);
-  }
-  CB_LAUNCH_CHECK();
-  return COGDL_B200_OK;
+static StreamParams to_stream(const SpmmParams &p) {
+  StreamParams q;
+  q.rowptr = p.rowptr; q.colind = p.colind; q.val = p.val; q.att = nullptr; q.perm = nullptr;
+  q.X0 = p.X0; q.X1 = p.X1; q.n0 = p.n0; q.Y = p.Y; q.ldv = p.FV; q.H = 1; q.FVL = p.FV; q.S = 1;
+  q.hub = p.hub;
+  return q;
 }
 
 template <typename VecT, int NV>
 static int launch_spmm_stream(const SpmmParams &p, cudaStream_t stream) {
+  const StreamParams q = to_stream(p);
+  const int mode = p.val ? MODE_WEIGHTED : MODE_UNWEIGHTED;
   if constexpr (NV == 1 && sizeof(VecT) == 16) {
     switch (spmm_variant()) {
-      case 0: return launch_spmm_stream_v<VecT, 1, 8, 1>(p, stream);
-      case 2: return launch_spmm_stream_v<VecT, 1, 4, 5>(p, stream);
-      case 3: return launch_spmm_stream_v<VecT, 1, 4, 6>(p, stream);
-      case 4: return launch_spmm_stream_v<VecT, 1, 16, 2>(p, stream);
-      default: return launch_spmm_stream_v<VecT, 1, 8, 4>(p, stream);  // 64 regs, 32 warps/SM: fastest measured (profiles/r01b_tune_spmm_stream.txt)
+      case 0: return launch_stream<VecT, 1, 8, 1>(q, mode, stream);
+      case 2: return launch_stream<VecT, 1, 4, 5>(q, mode, stream);
+      case 3: return launch_stream<VecT, 1, 4, 6>(q, mode, stream);
+      case 4: return launch_stream<VecT, 1, 16, 2>(q, mode, stream);
+      case 5: return launch_stream<VecT, 1, 8, 4, false>(q, mode, stream);
+      case 6: return launch_stream<VecT, 1, 8, 3>(q, mode, stream);
+      case 1: return launch_stream<VecT, 1, 8, 4>(q, mode, stream);
+      case 8: return launch_stream<VecT, 1, 4, 5, false, true>(q, mode, stream);   // + L2 evict_last hint on X
+      case 9: return launch_stream<VecT, 1, 8, 4, false, true>(q, mode, stream);
+      // U=4, 48 registers (40 warps/SM), no slab prefetch: fastest measured (profiles/r01d_tune_stream_v2.txt)
+      default: return launch_stream<VecT, 1, 4, 5, false>(q, mode, stream);
     }
   }
   constexpr int U = (NV == 1) ? 8 : (NV == 2 ? 4 : 2);
-  return launch_spmm_stream_v<VecT, NV, U, 1>(p, stream);
+  return launch_stream<VecT, NV, U, 1>(q, mode, stream);
 }
 
 template <typename VecT, int GROUP, int NV>

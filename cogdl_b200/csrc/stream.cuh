@@ -1,0 +1,226 @@
+// stream.cuh -- the row-stream gather kernel shared by the SpMM and the multi-head SpMM (sm_100a).
+//
+// Work items, in grid order:
+//   [0, n_chunks)                 hub chunks: <= chunk_edges edges of ONE hub row -> partial sum in
+//                                 scratch, combined in chunk order by the last chunk to arrive;
+//   [n_chunks, n_chunks+n_segs)   segments: runs of consecutive NON-hub rows (~seg_cost rows+edges).
+// In multi-head mode every item exists once per 512-byte slice of the [H*F] row (adjacent warps).
+//
+// One warp per item.  A segment's edges are contiguous in colind/val/edge_row, so the warp walks
+// them in 32-edge slabs: one coalesced load each for colind, the value (or permutation) and the
+// owning row; `row != row of the next edge` gives a 32-bit "row ends here" mask with one ballot.
+// Gathers are issued U at a time and are always full batches except at the segment tail, whatever
+// the row lengths (a row-per-warp kernel issues only `degree` gathers behind a rowptr -> colind -> X
+// dependent chain).  Per output element the accumulation is strictly in CSR order with separate
+// fp32 multiply and add => bit-identical to the reference CPU loop (spmm_cpu.cpp:24-36) for every
+// row that is not a hub.  At a set mask bit the accumulator is stored to its row and cleared.
+#pragma once
+#include "common.cuh"
+
+namespace cogdl_b200 {
+
+struct StreamParams {
+  const int *rowptr;
+  const int *colind;
+  const float *val;   // MODE 1: [nnz]
+  const float *att;   // MODE 2: [nnz, H]
+  const int *perm;    // MODE 2, nullable: attention row of edge p is perm[p]
+  const float *X0;
+  const float *X1;    // second source (two-source form), rows >= n0
+  int64_t n0;
+  float *Y;
+  int ldv;            // dense row length in VecT units
+  int H;              // MODE 2: heads
+  int FVL;            // MODE 2: VecT units per head
+  int S;              // MODE 2: 512-byte slices per row (1 otherwise)
+  HubView hub;
+};
+
+enum { MODE_UNWEIGHTED = 0, MODE_WEIGHTED = 1, MODE_MULTIHEAD = 2 };
+
+template <typename VecT> __device__ __forceinline__ VecT sk_zero();
+template <> __device__ __forceinline__ float4 sk_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ float sk_zero<float>() { return 0.f; }
+__device__ __forceinline__ void sk_add(float &a, const float &b) { a = __fadd_rn(a, b); }
+__device__ __forceinline__ void sk_add(float4 &a, const float4 &b) { add_rn(a, b); }
+
+// Stream the edge range [e, e_end).  ROWS: flush at row ends (segment); otherwise accumulate the
+// whole range into acc (hub chunk).
+template <typename VecT, int NV, int MODE, bool HAS_PERM, bool TWO_SRC, int U, bool ROWS, bool PREFETCH, bool HINT>
+__device__ __forceinline__ void stream_range(const StreamParams &p, int e, const int e_end, const int cv,
+                                             const bool (&colok)[NV], const int head, const int lane,
+                                             VecT (&acc)[NV]) {
+  const VecT *X0 = reinterpret_cast<const VecT *>(p.X0) + cv;
+  const VecT *X1 = reinterpret_cast<const VecT *>(p.X1) + cv;
+  VecT *Y = reinterpret_cast<VecT *>(p.Y) + cv;
+  const uint64_t pol = HINT ? l2_policy_evict_last() : 0;
+
+  // slab registers: column, value / attention row, owning row, owning row of the next edge
+  int c = 0, rid = -1, rnx = -1, pe = 0;
+  float v = 0.f;
+  auto load_slab = [&](int base, int &c_, float &v_, int &pe_, int &rid_, int &rnx_) {
+    const int q = base + lane;
+    c_ = 0; v_ = 0.f; pe_ = 0; rid_ = -1; rnx_ = -1;
+    if (q < e_end) {
+      c_ = ld_stream(p.colind + q);
+      if (MODE == MODE_WEIGHTED) v_ = ld_stream(p.val + q);
+      if (MODE == MODE_MULTIHEAD) pe_ = HAS_PERM ? ld_stream(p.perm + q) : q;
+      if (ROWS) {
+        rid_ = ld_stream(p.hub.edge_row + q);
+        if (q + 1 < e_end) rnx_ = __ldg(p.hub.edge_row + q + 1);
+      }
+    }
+  };
+  load_slab(e, c, v, pe, rid, rnx);
+
+  for (; e < e_end; e += 32) {
+    const int cnt = min(32, e_end - e);
+    const unsigned endmask = ROWS ? __ballot_sync(FULL, lane < cnt && rid != rnx) : 0u;
+    int cn, pn, ridn, rnxn;
+    float vn;
+    if (PREFETCH) load_slab(e + 32, cn, vn, pn, ridn, rnxn);  // next slab rides behind this slab's gathers
+
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += U) {
+      const bool full = (j + U <= cnt);
+      const unsigned em = endmask >> j;
+      VecT x[U][NV];
+      float a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cj = __shfl_sync(FULL, c, j + u);
+        const int pj = (MODE == MODE_MULTIHEAD) ? __shfl_sync(FULL, pe, j + u) : 0;
+        if (full || j + u < cnt) {
+          const VecT *xp = (!TWO_SRC || cj < p.n0) ? X0 + (int64_t)cj * p.ldv : X1 + ((int64_t)cj - p.n0) * p.ldv;
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (colok[k]) x[u][k] = HINT ? ld_gather_hint(xp + k * 32, pol) : ld_gather(xp + k * 32);
+          if (MODE == MODE_MULTIHEAD && colok[0]) a[u] = __ldg(p.att + (int64_t)pj * p.H + head);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float vj = (MODE == MODE_WEIGHTED) ? __shfl_sync(FULL, v, j + u) : 0.f;
+        const int rj = ROWS ? __shfl_sync(FULL, rid, j + u) : 0;
+        if (full || j + u < cnt) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            if (colok[k]) {
+              if (MODE == MODE_UNWEIGHTED) sk_add(acc[k], x[u][k]);          // 1.0f * x == x exactly
+              else if (MODE == MODE_WEIGHTED) axpy_rn(acc[k], vj, x[u][k]);
+              else axpy_rn(acc[k], a[u], x[u][k]);
+            }
+          }
+          if (ROWS && ((em >> u) & 1u)) {   // last edge of row rj: store and restart (warp-uniform)
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+              if (colok[k]) { st_stream(Y + (int64_t)rj * p.ldv + k * 32, acc[k]); acc[k] = sk_zero<VecT>(); }
+          }
+        }
+      }
+    }
+    if (PREFETCH) { c = cn; v = vn; pe = pn; rid = ridn; rnx = rnxn; }
+    else load_slab(e + 32, c, v, pe, rid, rnx);
+  }
+}
+
+template <typename VecT, int NV, int MODE, bool HAS_PERM, bool TWO_SRC, int U, int MINB, bool PREFETCH, bool HINT>
+__global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p) {
+  constexpr int TILE = 32 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t item = (MODE == MODE_MULTIHEAD) ? wid / p.S : wid;
+  const int slice = (MODE == MODE_MULTIHEAD) ? (int)(wid - item * p.S) : 0;
+  VecT *Y = reinterpret_cast<VecT *>(p.Y);
+  VecT *P = reinterpret_cast<VecT *>(p.hub.partials);
+
+  // column tiles: the multi-head form owns exactly one 32-vector slice; the plain form loops over
+  // the row in TILE-vector passes (one pass for F <= 128 * NV)
+  const int t_begin = (MODE == MODE_MULTIHEAD) ? slice * 32 : 0;
+  const int t_end = (MODE == MODE_MULTIHEAD) ? t_begin + 1 : p.ldv;
+
+  if (item < p.hub.n_chunks) {
+    const WorkItem w = decode_item(item, 0, p.rowptr, p.hub);
+    for (int tile0 = t_begin; tile0 < t_end; tile0 += TILE) {
+      const int cv = tile0 + lane;
+      bool colok[NV];
+      VecT acc[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { colok[k] = (cv + k * 32) < p.ldv; acc[k] = sk_zero<VecT>(); }
+      const int head = (MODE == MODE_MULTIHEAD && colok[0]) ? cv / p.FVL : 0;
+      stream_range<VecT, NV, MODE, HAS_PERM, TWO_SRC, U, false, PREFETCH, HINT>(p, w.lb, w.hb, cv, colok, head, lane, acc);
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        if (colok[k]) st_cg(P + (int64_t)w.slot * p.ldv + cv + k * 32, acc[k]);
+    }
+    WorkItem wa = w;
+    wa.n_row_chunks = w.n_row_chunks * p.S;   // every slice of every chunk arrives once
+    if (hub_arrive_last<32>(wa, p.hub, lane)) {
+      for (int cv = lane; cv < p.ldv; cv += 32) {
+        const VecT *pp = P + (int64_t)w.first * p.ldv + cv;
+        VecT s = ld_cg(pp);
+        for (int q = 1; q < w.n_row_chunks; ++q) sk_add(s, ld_cg(pp + (int64_t)q * p.ldv));
+        st_stream(Y + (int64_t)w.row * p.ldv + cv, s);
+      }
+    }
+    return;
+  }
+
+  const int64_t seg = item - p.hub.n_chunks;
+  if (seg >= p.hub.n_segs) return;
+  const int2 rr = __ldg(p.hub.segs + seg);
+  const int e_begin = __ldg(p.rowptr + rr.x), e_end = __ldg(p.rowptr + rr.y);
+
+  for (int tile0 = t_begin; tile0 < t_end; tile0 += TILE) {
+    const int cv = tile0 + lane;
+    bool colok[NV];
+    VecT acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { colok[k] = (cv + k * 32) < p.ldv; acc[k] = sk_zero<VecT>(); }
+    const int head = (MODE == MODE_MULTIHEAD && colok[0]) ? cv / p.FVL : 0;
+    if (p.hub.n_empty_rows > 0) {
+      // rows without edges never show up in the edge stream: zero-fill them here
+      for (int rb = rr.x; rb < rr.y; rb += 32) {
+        const int row = rb + lane;
+        unsigned m = __ballot_sync(FULL, row < rr.y && __ldg(p.rowptr + row + 1) == __ldg(p.rowptr + row));
+        while (m) {
+          const int k0 = __ffs(m) - 1;
+          m &= m - 1;
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (colok[k]) st_stream(Y + (int64_t)(rb + k0) * p.ldv + cv + k * 32, sk_zero<VecT>());
+        }
+      }
+    }
+    stream_range<VecT, NV, MODE, HAS_PERM, TWO_SRC, U, true, PREFETCH, HINT>(p, e_begin, e_end, cv, colok, head, lane, acc);
+  }
+}
+
+// Launch helper: picks the instantiation for (mode, perm, two-source); U / MINB fixed by the caller.
+template <typename VecT, int NV, int U, int MINB, bool PREFETCH = true, bool HINT = false>
+static int launch_stream(const StreamParams &p, int mode, cudaStream_t stream) {
+  const int64_t warps = ((int64_t)p.hub.n_chunks + p.hub.n_segs) * p.S;
+  const int64_t blocks = ceil_div(warps * 32, 256);
+  if (blocks == 0) return COGDL_B200_OK;
+  if (blocks > 0x7fffffffLL) return set_error(COGDL_B200_EINVAL, "stream kernel: problem too large for one launch");
+  const unsigned g = (unsigned)blocks;
+  const bool two = p.n0 != INT64_MAX;
+  if (mode == MODE_MULTIHEAD) {
+    if constexpr (NV == 1) {
+      if (p.perm) stream_kernel<VecT, 1, MODE_MULTIHEAD, true, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+      else stream_kernel<VecT, 1, MODE_MULTIHEAD, false, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    } else {
+      return set_error(COGDL_B200_EINVAL, "stream kernel: multi-head form needs NV == 1");
+    }
+  } else if (mode == MODE_WEIGHTED) {
+    if (two) stream_kernel<VecT, NV, MODE_WEIGHTED, false, true, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    else stream_kernel<VecT, NV, MODE_WEIGHTED, false, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+  } else {
+    if (two) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, true, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    else stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+  }
+  CB_LAUNCH_CHECK();
+  return COGDL_B200_OK;
+}
+
+}  // namespace cogdl_b200

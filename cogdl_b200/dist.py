@@ -1,0 +1,209 @@
+"""Node-range partitioned SpMM across the GPUs of one box (new functionality -- the
+reference's sparse ops are single-GPU only).
+
+One process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).  Rank p owns a contiguous
+range of destination rows [lo_p, hi_p) of A together with the matching rows of X and Y.  Output
+rows are independent, so the only coupling is the gather of X rows owned by other ranks:
+
+    setup (once per structure)   columns outside [lo_p, hi_p) are renumbered to n_local + k where k
+                                 indexes this rank's sorted, de-duplicated halo list; the halo lists
+                                 are exchanged so every owner knows which of its rows each peer needs
+    step                         pack   : send_buf = X_local[send_index]          (gather kernel)
+                                 move   : all-to-all of the packed rows over NVLink (NCCL)
+                                 compute: Y_local = A_local @ [X_local ; X_halo]   (two-source SpMM,
+                                          cogdl_b200_spmm_csr_f32_2src -- no concatenation copy)
+
+This is the pull form of the boundary exchange; the push form ("all-reduce of boundary partial
+sums", north star) moves the same order of bytes -- (#distinct remote rows) * 4F per rank -- but
+needs the column-sliced matrix and an extra reduction pass, so the pull form is what is built.
+There is no all-reduce on the data path: a row's sum is completed by exactly one rank.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import synth
+from .structure import CSRStructure
+
+
+def balanced_row_ranges(row_ptr, parts):
+    """Contiguous row ranges balanced by cost = nnz + rows (power-law graphs: NOT by row count)."""
+    n = row_ptr.numel() - 1
+    cost = row_ptr.to(torch.int64) + torch.arange(n + 1, device=row_ptr.device, dtype=torch.int64)
+    total = int(cost[-1])
+    targets = torch.tensor([total * k // parts for k in range(parts + 1)], device=row_ptr.device, dtype=torch.int64)
+    bounds = torch.searchsorted(cost, targets).clamp_(max=n)
+    bounds[0], bounds[-1] = 0, n
+    return [int(b) for b in bounds.tolist()]
+
+
+class LocalPartition:
+    """What one rank holds of the partitioned graph (index arithmetic only; device agnostic)."""
+
+    def __init__(self, rank, world, bounds, row_ptr_local, col_global, val_local):
+        self.rank, self.world, self.bounds = rank, world, list(bounds)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        self.lo, self.hi, self.n_local = lo, hi, hi - lo
+        col_global = col_global.to(torch.int64)
+        is_local = (col_global >= lo) & (col_global < hi)
+        remote = col_global[~is_local]
+        self.halo = torch.unique(remote)                                # sorted global ids this rank must fetch
+        self.n_halo = int(self.halo.numel())
+        col_local = torch.empty_like(col_global)
+        col_local[is_local] = col_global[is_local] - lo
+        col_local[~is_local] = self.n_local + torch.searchsorted(self.halo, remote)
+        self.row_ptr = row_ptr_local
+        self.col = col_local
+        self.val = val_local
+        self.nnz_local = int(col_global.numel())
+        bt = torch.tensor(self.bounds, device=self.halo.device, dtype=torch.int64)
+        owner = torch.searchsorted(bt, self.halo, right=True) - 1       # owner rank of every halo row
+        self.recv_counts = torch.bincount(owner, minlength=world).tolist()   # rows I receive from each rank
+        self.halo_owner_local = self.halo - bt[owner]                   # row index inside the owner's shard
+
+
+def exchange_index_lists(part, group=None):
+    """Tell every owner which of its rows this rank needs.  Returns (send_index, send_counts):
+    send_index = my local row ids to pack, concatenated in peer order."""
+    world = part.world
+    dev = part.halo.device
+    recv_counts = torch.tensor(part.recv_counts, dtype=torch.int64, device=dev)
+    send_counts = torch.empty(world, dtype=torch.int64, device=dev)
+    _all_to_all(send_counts, recv_counts, [1] * world, [1] * world, group)
+    send_counts_l = [int(v) for v in send_counts.tolist()]
+    send_index = torch.empty(sum(send_counts_l), dtype=torch.int64, device=dev)
+    _all_to_all(send_index, part.halo_owner_local.contiguous(), send_counts_l, part.recv_counts, group)
+    return send_index, send_counts_l
+
+
+def _all_to_all(out, inp, out_splits, in_splits, group=None):
+    """all_to_all_single on NCCL; point-to-point batch on backends without it (gloo in CPU tests)."""
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    outs = list(out.split(out_splits)) if sum(out_splits) else [out[:0]] * world
+    ins = list(inp.split(in_splits)) if sum(in_splits) else [inp[:0]] * world
+    outs[rank].copy_(ins[rank])
+    ops = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if in_splits[peer]:
+            ops.append(dist.P2POp(dist.isend, ins[peer].contiguous(), peer, group))
+        if out_splits[peer]:
+            ops.append(dist.P2POp(dist.irecv, outs[peer], peer, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+class PartitionedSpMM:
+    """Per-rank state + the step: y_local = spmm(x_local) with the halo exchange inside."""
+
+    def __init__(self, part: LocalPartition, device, group=None, global_nnz=None, description=""):
+        self.part, self.device, self.group = part, device, group
+        self.n_local, self.n_halo, self.nnz_local = part.n_local, part.n_halo, part.nnz_local
+        self.send_index, self.send_counts = exchange_index_lists(part, group)
+        self.recv_counts = part.recv_counts
+        self.global_nnz = global_nnz
+        self.exchange = "NCCL all_to_all_single" if dist.get_backend(group) == "nccl" else "p2p"
+        self._desc = description
+        if device.type == "cuda":
+            self.st = CSRStructure.from_int64(part.row_ptr.to(device), part.col.to(device),
+                                              n_cols=part.n_local + part.n_halo)
+            self.st.plan
+            self.val = None if part.val is None else part.val.to(device).float().contiguous()
+            self.send_index32 = self.send_index.to(device).to(torch.int32).contiguous()
+        self.x_local = None
+
+    def describe(self):
+        return self._desc
+
+    # -- the three stages, separately callable (tests / profiling)
+    def pack(self, x_local):
+        if x_local.is_cuda:
+            from .operators._raw import gather_rows_raw
+
+            return gather_rows_raw(self.send_index32, x_local)
+        return x_local.index_select(0, self.send_index)   # host tensors: gloo plumbing tests only
+
+    def exchange_rows(self, send_buf, F):
+        halo = torch.empty((self.n_halo, F), dtype=send_buf.dtype, device=send_buf.device)
+        _all_to_all(halo.view(-1), send_buf.view(-1), [c * F for c in self.recv_counts],
+                    [c * F for c in self.send_counts], self.group)
+        return halo
+
+    def local_spmm(self, x_local, x_halo):
+        from .operators._raw import spmm_2src_raw
+
+        return spmm_2src_raw(self.st, self.val, x_local, x_halo)
+
+    def spmm(self, x_local):
+        F = x_local.shape[1]
+        halo = self.exchange_rows(self.pack(x_local), F)
+        return self.local_spmm(x_local, halo)
+
+    def last_kernel_seconds(self, step, torch_mod, iters=5):
+        """Mean duration of the local two-source SpMM kernel alone (CUDA events), for the roofline."""
+        F = self.x_local.shape[1]
+        halo = self.exchange_rows(self.pack(self.x_local), F)
+        for _ in range(2):
+            self.local_spmm(self.x_local, halo)
+        a, b = torch_mod.cuda.Event(enable_timing=True), torch_mod.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            self.local_spmm(self.x_local, halo)
+        b.record()
+        torch_mod.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / iters / 1e3], device=self.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t)
+
+
+def partition_global_csr(row_ptr, col, val, rank, world, device, group=None):
+    """Slice a (replicated, host or device) global CSR into this rank's LocalPartition."""
+    bounds = balanced_row_ranges(row_ptr, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    e0, e1 = int(row_ptr[lo]), int(row_ptr[hi])
+    part = LocalPartition(rank, world, bounds, (row_ptr[lo:hi + 1] - e0).clone(), col[e0:e1].clone(),
+                          None if val is None else val[e0:e1].clone())
+    return PartitionedSpMM(part, device, group, global_nnz=int(row_ptr[-1]))
+
+
+# papers100M-shaped graph, 1/8 of it per GPU (BASELINE configs[4]): fixed per-GPU work => weak scaling
+PAPERS_ROWS_PER_GPU = synth.SHAPES["papers100M"][0] // 8      # 13 882 494
+PAPERS_EDGES_PER_GPU = synth.SHAPES["papers100M"][1] // 8     # 201 960 734
+
+
+def synthetic_partition(rank, world, device, seed=0, rows=PAPERS_ROWS_PER_GPU, edges=PAPERS_EDGES_PER_GPU,
+                        beta=0.05, hidden=128, group=None):
+    """Generate this rank's shard directly on its GPU: power-law degrees inside the shard, a column is
+    uniform over the WHOLE graph with probability beta (remote with prob. beta*(P-1)/P) and uniform
+    inside the own range otherwise (the locality-controlled generator of SURVEY 8d)."""
+    n_total = rows * world
+    lo = rank * rows
+    deg, g = synth.powerlaw_degrees(rows, edges, seed=seed * 1000 + rank, device=device)
+    row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=row_ptr[1:])
+    del deg
+    col = torch.empty(edges, dtype=torch.int64, device=device)
+    chunk = 1 << 26
+    for s in range(0, edges, chunk):
+        m = min(chunk, edges - s)
+        local = lo + torch.randint(0, rows, (m,), generator=g, device=device)
+        anywhere = torch.randint(0, n_total, (m,), generator=g, device=device)
+        remote = torch.rand(m, generator=g, device=device) < beta
+        col[s:s + m] = torch.where(remote, anywhere, local)
+        del local, anywhere, remote
+    bounds = [k * rows for k in range(world + 1)]
+    part = LocalPartition(rank, world, bounds, row_ptr, col, None)
+    del col
+    desc = (f"unweighted spmm hidden={hidden} (fp32), papers100M-shaped power-law CSR partitioned by node range: "
+            f"{rows} rows + {edges} edges per GPU x {world} GPUs (= {n_total} nodes, {edges * world} edges), "
+            f"columns remote-eligible with prob beta={beta}, seed {seed} [BASELINE configs[4] shape, 1/8 of papers100M per GPU]")
+    ps = PartitionedSpMM(part, device, group, global_nnz=edges * world, description=desc)
+    ps.x_local = torch.randn(rows, hidden, device=device, generator=torch.Generator(device=device).manual_seed(seed + rank))
+    return ps

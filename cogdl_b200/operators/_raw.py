@@ -170,8 +170,7 @@ def gat_fwd_raw(st: CSRStructure, h_l, h_r, feat, slope, want_att):
     H, F = feat.shape[1], feat.shape[2]
     with torch.cuda.device(dev):
         out = torch.empty((st.n_rows, H, F), dtype=torch.float32, device=dev)
-        need_att = want_att or (st.chunk_edges > 0 and st.plan.n_chunks > 0)
-        att = torch.empty((st.nnz, H), dtype=torch.float32, device=dev) if need_att else None
+        att = torch.empty((st.nnz, H), dtype=torch.float32, device=dev)   # output for training, scratch otherwise
         plan, keep = st.plan_struct(st.plan.n_chunks * H * F * 4 if st.chunk_edges > 0 else 0)
         _cabi.call("cogdl_b200_gat_fwd_f32", _ptr(st.rowptr), _ptr(st.colind), _ptr(h_l), _ptr(h_r), _ptr(feat),
                    float(slope), _ptr(out), _ptr(att), st.n_rows, H, F, plan, _stream(dev))

@@ -17,7 +17,7 @@ from . import _cabi
 import os
 
 # rows with more edges than this are cut into chunks of this many edges (hub plan)
-DEFAULT_CHUNK_EDGES = int(os.environ.get("COGDL_B200_CHUNK_EDGES", "128"))
+DEFAULT_CHUNK_EDGES = int(os.environ.get("COGDL_B200_CHUNK_EDGES", "64"))
 # rows + edges streamed by one warp of the row-stream kernels (0 disables the stream form)
 DEFAULT_SEG_COST = int(os.environ.get("COGDL_B200_SEG_COST", "128"))
 
@@ -69,24 +69,29 @@ class HubPlan:
         n_rows = rowptr32.numel() - 1
         self.chunk_edges = int(chunk_edges)
         self.seg_cost = int(DEFAULT_SEG_COST if seg_cost is None else seg_cost)
-        self.n_segs, self.seg_starts = 0, None
+        if nnz is None or n_rows == 0:
+            self.seg_cost = 0
         self.device = dev
+        self.segs = self.edge_row = None
         with torch.cuda.device(dev):
-            counts = torch.empty(2, dtype=torch.int32, device=dev)
-            _cabi.call("cogdl_b200_hub_plan_count", _ptr(rowptr32), n_rows, self.chunk_edges, _ptr(counts), _stream(dev))
-            n_hub, n_chunks = (int(v) for v in counts.tolist())  # one sync per structure
-            self.n_hub_rows, self.n_chunks = n_hub, n_chunks
+            counts = torch.empty(4, dtype=torch.int32, device=dev)
+            _cabi.call("cogdl_b200_hub_plan_count", _ptr(rowptr32), n_rows, self.chunk_edges, self.seg_cost,
+                       _ptr(counts), _stream(dev))
+            n_hub, n_chunks, n_empty, n_segs = (int(v) for v in counts.tolist())  # one sync per structure
+            self.n_hub_rows, self.n_chunks, self.n_empty_rows, self.n_segs = n_hub, n_chunks, n_empty, n_segs
             self.hub_rows = torch.empty(max(n_hub, 1), dtype=torch.int32, device=dev)
             self.chunks = torch.empty(max(2 * n_chunks, 2), dtype=torch.int32, device=dev)
             self.counters = torch.zeros(max(n_chunks, 1), dtype=torch.int32, device=dev)
-            if n_chunks > 0:
-                _cabi.call("cogdl_b200_hub_plan_fill", _ptr(rowptr32), n_rows, self.chunk_edges, _ptr(counts),
-                           _ptr(self.hub_rows), _ptr(self.chunks), _stream(dev))
-            if nnz is not None and self.seg_cost > 0 and n_rows > 0:
-                self.n_segs = (int(nnz) + n_rows + self.seg_cost - 1) // self.seg_cost
-                self.seg_starts = torch.empty(self.n_segs + 1, dtype=torch.int32, device=dev)
-                _cabi.call("cogdl_b200_hub_plan_segments", _ptr(rowptr32), n_rows, self.seg_cost, self.n_segs,
-                           _ptr(self.seg_starts), _stream(dev))
+            if self.seg_cost > 0 and n_segs > 0:
+                self.segs = torch.empty(2 * n_segs, dtype=torch.int32, device=dev)
+                self.edge_row = torch.empty(int(nnz), dtype=torch.int32, device=dev)
+                _cabi.call("cogdl_b200_edge_rows", _ptr(rowptr32), n_rows, int(nnz), _ptr(self.edge_row), _stream(dev))
+            else:
+                self.n_segs = 0
+            if n_chunks > 0 or self.n_segs > 0:
+                _cabi.call("cogdl_b200_hub_plan_fill", _ptr(rowptr32), n_rows, self.chunk_edges,
+                           self.seg_cost if self.segs is not None else 0, _ptr(counts), _ptr(self.hub_rows),
+                           _ptr(self.chunks), _ptr(self.segs), _stream(dev))
 
     def struct(self, partial_bytes=0):
         """ctypes struct for one call; partial scratch comes from torch's caching allocator.
@@ -98,8 +103,10 @@ class HubPlan:
         s.hub_rows = self.hub_rows.data_ptr()
         s.chunks = self.chunks.data_ptr()
         s.counters = self.counters.data_ptr()
-        if self.seg_starts is not None:
-            s.seg_cost, s.n_segs, s.seg_starts = self.seg_cost, self.n_segs, self.seg_starts.data_ptr()
+        s.n_empty_rows = self.n_empty_rows
+        if self.segs is not None:
+            s.seg_cost, s.n_segs = self.seg_cost, self.n_segs
+            s.segs, s.edge_row = self.segs.data_ptr(), self.edge_row.data_ptr()
         scratch = None
         if self.n_chunks > 0 and partial_bytes > 0:
             scratch = torch.empty((partial_bytes + 15) // 16 * 4, dtype=torch.float32, device=self.device)

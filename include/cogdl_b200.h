@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define COGDL_B200_ABI_VERSION 2
+#define COGDL_B200_ABI_VERSION 3
 
 #define COGDL_B200_OK 0
 #define COGDL_B200_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
@@ -76,34 +76,36 @@ typedef struct cogdl_b200_hub_plan {
   int32_t chunk_edges;
   int32_t n_hub_rows;
   int32_t n_chunks;
-  int32_t reserved;
+  int32_t n_empty_rows;      /* rows of degree 0 (the row-stream kernels zero-fill them) */
   const int32_t *hub_rows;
   const int32_t *chunks;
   int32_t *counters;
   void *partials;
   int64_t partials_bytes;
-  /* Row-stream segments (optional, seg_starts == NULL => one warp per row): segment k is the run
-   * of consecutive rows [seg_starts[k], seg_starts[k+1]) whose cumulative cost rowptr[r] + r starts
-   * inside [k*seg_cost, (k+1)*seg_cost); one warp streams a segment's edges with full gather
-   * batches and flushes at row boundaries.  n_segs = ceil((nnz + n_rows) / seg_cost). */
+  /* Row-stream segments (optional; segs == NULL => one warp per row).  A segment is a run of
+   * consecutive NON-hub rows [row_begin, row_end) of roughly seg_cost rows+edges; its edges are
+   * contiguous in colind, so one warp streams them in coalesced 32-edge slabs with always-full
+   * gather batches and flushes its accumulator at row ends.  edge_row[p] = row owning edge p
+   * (the COO row array) lets the kernel find row ends with one ballot per slab. */
   int32_t seg_cost;
   int32_t n_segs;
-  const int32_t *seg_starts; /* [n_segs + 1] */
+  const int32_t *segs;     /* [2*n_segs] (row_begin, row_end), any order */
+  const int32_t *edge_row; /* [nnz] */
 } cogdl_b200_hub_plan_t;
 
-/* Pass 1: counts_dev[0] = #rows with degree > chunk_edges, counts_dev[1] = #chunks.
- * counts_dev is a 2-int device buffer (zeroed by the call). */
+/* Pass 1: counts_dev[0..3] = #rows with degree > chunk_edges, #chunks, #empty rows, #segments
+ * (for seg_cost; pass seg_cost <= 0 to skip segments).  counts_dev: 4-int device buffer. */
 COGDL_B200_API int cogdl_b200_hub_plan_count(const int32_t *rowptr, int64_t n_rows, int32_t chunk_edges,
-                              int32_t *counts_dev, cogdl_b200_stream_t stream);
-/* Pass 2: fills hub_rows[counts[0]] and chunks[2*counts[1]] (caller-allocated from pass 1's
- * counts); counts_dev is reused as the slot allocator (zeroed by the call). */
+                              int32_t seg_cost, int32_t *counts_dev, cogdl_b200_stream_t stream);
+/* Pass 2: fills hub_rows[counts[0]], chunks[2*counts[1]] and segs[2*counts[3]] (caller-allocated
+ * from pass 1's counts; segs may be NULL with seg_cost <= 0); counts_dev is reused as allocator. */
 COGDL_B200_API int cogdl_b200_hub_plan_fill(const int32_t *rowptr, int64_t n_rows, int32_t chunk_edges,
-                             int32_t *counts_dev, int32_t *hub_rows, int32_t *chunks,
-                             cogdl_b200_stream_t stream);
-
-/* seg_starts[k] = first row r with rowptr[r] + r >= k*seg_cost, k = 0..n_segs (n_segs + 1 ints). */
-COGDL_B200_API int cogdl_b200_hub_plan_segments(const int32_t *rowptr, int64_t n_rows, int32_t seg_cost,
-                                 int32_t n_segs, int32_t *seg_starts, cogdl_b200_stream_t stream);
+                             int32_t seg_cost, int32_t *counts_dev, int32_t *hub_rows, int32_t *chunks,
+                             int32_t *segs, cogdl_b200_stream_t stream);
+/* edge_row[p] = row owning CSR position p (CSR -> COO row expansion; reference keeps the same
+ * array as Adjacency.row, cogdl/data/data.py:136). */
+COGDL_B200_API int cogdl_b200_edge_rows(const int32_t *rowptr, int64_t n_rows, int64_t nnz, int32_t *edge_row,
+                         cogdl_b200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * CSR SpMM   Y[i,:] = sum_{p in row i} val[p] * X[colind[p],:]        (val == NULL => 1)
@@ -220,10 +222,12 @@ COGDL_B200_API int cogdl_b200_scatter_max_bwd_f32(const float *g, const int32_t 
 /* ---------------------------------------------------------------------------------------
  * "Next" rows.
  *
- * Fused GAT forward: e = leakyrelu(h_l[i,h] + h_r[col,h]); a = softmax_row(e); out = sum a*feat.
- * The [nnz,H] logits/attention are never materialised unless att_out != NULL (training saves
- * them for the backward).  Replaces the unfused chain cogdl/layers/gat_layer.py:73-77 and the
- * stale dgNN binding cogdl/operators/fused_gat.py:17-19.
+ * GAT forward: e = leakyrelu(h_l[i,h] + h_r[col,h]); a = softmax_row(e); out = sum a*feat.
+ * The logits are formed and soft-maxed in registers (no [nnz,H] gather / add / activation
+ * temporaries); the normalised attention is written once to att_out ([nnz,H], required: it is the
+ * saved tensor of the backward and the operand of the row-stream multi-head SpMM that follows).
+ * Replaces the unfused chain cogdl/layers/gat_layer.py:73-77 and the stale dgNN binding
+ * cogdl/operators/fused_gat.py:17-19.
  * ------------------------------------------------------------------------------------- */
 COGDL_B200_API int cogdl_b200_gat_fwd_f32(const int32_t *rowptr, const int32_t *colind, const float *h_l,
                            const float *h_r, const float *feat, float negative_slope, float *out,

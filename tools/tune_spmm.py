@@ -39,6 +39,21 @@ st = cogdl_b200.CSRStructure.from_int64(rp, col, n_cols=n)
 x = torch.randn(n, 128, device=dev)
 # cudaEvent timing of a single launch includes launch latency; subtract nothing, just report
 med, mn = timeit(lambda: spmm_raw(st, w, x))
+if shape == "arxiv" and os.environ.get("TUNE_EXTRA"):
+    from cogdl_b200.operators._raw import mhspmm_raw, edge_softmax_fwd_raw
+    H = 8
+    logits = (torch.randn(st.nnz, H, device=dev) * 3).clamp_(-10, 10)
+    m1, _ = timeit(lambda: edge_softmax_fwd_raw(st, logits), 10)
+    att = edge_softmax_fwd_raw(st, logits)
+    h = torch.randn(n, H, 128, device=dev)
+    m2, _ = timeit(lambda: mhspmm_raw(st, att, h), 10)
+    h16 = torch.randn(n, H, 16, device=dev)
+    m3, _ = timeit(lambda: mhspmm_raw(st, att, h16), 10)
+    from cogdl_b200.operators._raw import gat_fwd_raw, edge_softmax_bwd_raw
+    hl, hr = torch.randn(n, H, device=dev), torch.randn(n, H, device=dev)
+    m4, _ = timeit(lambda: gat_fwd_raw(st, hl, hr, h, 0.2, False), 10)
+    m5, _ = timeit(lambda: edge_softmax_bwd_raw(st, att, logits), 10)
+    print(f"RESULT extra edge_softmax_H8_us={m1*1e3:.1f} edge_softmax_bwd_us={m5*1e3:.1f} mhspmm_H8_F128_us={m2*1e3:.1f} mhspmm_H8_F16_us={m3*1e3:.1f} gat_fwd_H8_F128_us={m4*1e3:.1f}")
 print(f"RESULT {shape} variant={os.environ.get('COGDL_B200_SPMM_VARIANT','0')} seg={os.environ.get('COGDL_B200_SEG_COST')} chunk={os.environ.get('COGDL_B200_CHUNK_EDGES')} median_us={med*1e3:.1f} min_us={mn*1e3:.1f} nnz={st.nnz} segs={st.plan.n_segs} chunks={st.plan.n_chunks}")
 '''
 
@@ -52,12 +67,11 @@ def run(shape, variant, seg, chunk):
         print("FAILED", shape, variant, seg, chunk, r.stderr[-500:], flush=True)
 
 if __name__ == "__main__":
-    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    os.environ["TUNE_EXTRA"] = "1"
+    run("arxiv", 7, 128, 64)
+    os.environ.pop("TUNE_EXTRA")
     for shape in ("arxiv", "products"):
-        run(shape, 0, 0, 256)          # old row-per-warp kernel (no segments)
-        for variant in (0, 1, 2, 3, 4):
-            run(shape, variant, 96, 256)
-        best_grid = [(48, 256), (64, 256), (128, 256), (192, 256), (96, 128), (96, 512), (256, 512), (64, 128)]
-        for seg, chunk in best_grid:
-            for variant in ((0, 1) if not quick else (1,)):
-                run(shape, variant, seg, chunk)
+        for variant in (7, 8, 5, 9):
+            run(shape, variant, 128, 64)
+        run(shape, 8, 128, 128)
+        run(shape, 7, 128, 128)
