@@ -63,18 +63,20 @@ class LocalPartition:
         self.halo_owner_local = self.halo - bt[owner]                   # row index inside the owner's shard
 
 
-def exchange_index_lists(part, group=None):
+def exchange_index_lists(part, group=None, comm_device=None):
     """Tell every owner which of its rows this rank needs.  Returns (send_index, send_counts):
-    send_index = my local row ids to pack, concatenated in peer order."""
+    send_index = my local row ids to pack, concatenated in peer order.  comm_device: where the
+    (small) index lists live during the exchange -- NCCL needs CUDA tensors even when the
+    partition was computed on the host."""
     world = part.world
-    dev = part.halo.device
+    dev = part.halo.device if comm_device is None else comm_device
     recv_counts = torch.tensor(part.recv_counts, dtype=torch.int64, device=dev)
     send_counts = torch.empty(world, dtype=torch.int64, device=dev)
     _all_to_all(send_counts, recv_counts, [1] * world, [1] * world, group)
     send_counts_l = [int(v) for v in send_counts.tolist()]
     send_index = torch.empty(sum(send_counts_l), dtype=torch.int64, device=dev)
-    _all_to_all(send_index, part.halo_owner_local.contiguous(), send_counts_l, part.recv_counts, group)
-    return send_index, send_counts_l
+    _all_to_all(send_index, part.halo_owner_local.to(dev).contiguous(), send_counts_l, part.recv_counts, group)
+    return send_index.to(part.halo.device), send_counts_l
 
 
 def _all_to_all(out, inp, out_splits, in_splits, group=None):
@@ -106,7 +108,8 @@ class PartitionedSpMM:
     def __init__(self, part: LocalPartition, device, group=None, global_nnz=None, description=""):
         self.part, self.device, self.group = part, device, group
         self.n_local, self.n_halo, self.nnz_local = part.n_local, part.n_halo, part.nnz_local
-        self.send_index, self.send_counts = exchange_index_lists(part, group)
+        comm_dev = device if dist.get_backend(group) == "nccl" else None
+        self.send_index, self.send_counts = exchange_index_lists(part, group, comm_dev)
         self.recv_counts = part.recv_counts
         self.global_nnz = global_nnz
         self.exchange = "NCCL all_to_all_single" if dist.get_backend(group) == "nccl" else "p2p"
