@@ -312,6 +312,8 @@ def run_ours(args):
     dist_on = world > 1
     if dist_on:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     import cogdl_b200
     from cogdl_b200 import _cabi
@@ -358,9 +360,9 @@ def run_ours(args):
     else:
         from cogdl_b200 import dist as cdist
 
-        part = cdist.synthetic_partition(rank, world, dev, seed=0)
+        part = cdist.synthetic_partition(rank, world, dev, seed=0, mode=os.environ.get("COGDL_B200_DIST_MODE"))
         workload = part.describe()
-        x_dev = part.x_local
+        x_dev = part.x_local                       # p2p mode: already inside the symmetric shard
         step = lambda: part.spmm(x_dev)
         l0 = _cabi.launch_count()
         sampler.start()
@@ -369,7 +371,7 @@ def run_ours(args):
         launches_dev = _cabi.launch_count() - l0
         x_pin = x_dev.cpu().pin_memory()
         y_pin = torch.empty(part.n_local, F_HIDDEN).pin_memory()
-        x_in = torch.empty_like(x_dev)
+        x_in = x_dev if part.mode == "p2p" else torch.empty_like(x_dev)   # H2D lands in the shard itself
 
         def e2e_step():
             x_in.copy_(x_pin, non_blocking=True)
@@ -382,7 +384,7 @@ def run_ours(args):
         total_units = part.global_nnz
         n, nnz = part.n_local, part.nnz_local
         algo, bmin = spmm_bytes(n, nnz, F_HIDDEN, weighted=False)  # per rank, per launch
-        parallelism = f"node-range partition x{world}, halo exchange ({part.exchange}), no reduce"
+        parallelism = f"node-range partition x{world}; {part.exchange}; no reduce on the data path"
         h2d = d2h = part.n_local * F_HIDDEN * 4
 
     t = sum(ms) / len(ms) / 1e3
@@ -400,13 +402,15 @@ def run_ours(args):
         "algorithmic_GBps": achieved,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": TRAFFIC_BYTES_PER_LAUNCH if not dist_on else None,
-                     "peak_source": peak_src, "kernel": "cogdl_b200::spmm_kernel<float4,32,1,true>",
+                     "peak_source": peak_src, "kernel": "cogdl_b200::stream_kernel<float4, NV=1, weighted, U=4> (row-stream SpMM)" if not dist_on else
+                               "cogdl_b200::stream_kernel<float4, NV=1, unweighted, peers|two-source, U=4>",
                      "algorithmic_bytes_per_launch": algo, "compulsory_bytes_per_launch": bmin,
                      "frac_compulsory": bmin / kernel_t / 1e9 / peak,
                      "l2_resident": (not dist_on),
                      "note": "X (87 MB) fits the 126 MB L2, so algorithmic bytes/time may exceed the HBM peak; "
                              "frac_compulsory is the DRAM-side fraction" if not dist_on else
-                             "per-rank local SpMM kernel; X shard + halo exceed L2"},
+                             "per-rank SpMM kernel (max over ranks), X shard 7.1 GB >> L2; in p2p mode the same kernel "
+                             "also performs the remote-row gather over NVLink"},
         "e2e": {"value": total_units / t_e2e, "unit": "edges/s", "ms_per_step": t_e2e * 1e3,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "pinned host X -> device, cogdl_b200.spmm(graph, x), Y -> pinned host; CSR resident"},

@@ -154,7 +154,7 @@ static int dispatch_mh(MhParams &p, cudaStream_t s) {
     StreamParams q;
     q.rowptr = p.rowptr; q.colind = p.colind; q.val = nullptr; q.att = p.att; q.perm = p.perm;
     q.X0 = p.feat; q.X1 = p.feat; q.n0 = INT64_MAX; q.Y = p.out; q.ldv = p.HFV; q.H = p.H; q.FVL = p.FVL;
-    q.S = p.S; q.hub = p.hub;
+    q.S = p.S; q.hub = p.hub; q.n_peers = 0; q.peer_shift = 0;
     if (p.n_rows == 0) q.hub.n_segs = 0;   // chunks-only call (fused GAT hub path)
     return launch_stream<VecT, 1, 8, 3>(q, MODE_MULTIHEAD, s);
   }

@@ -33,6 +33,9 @@
 namespace cogdl_b200 {
 
 struct SpmmParams {
+  const float *peers[8];
+  int n_peers;
+  int peer_shift;
   const int *rowptr;
   const int *colind;
   const float *val;
@@ -181,6 +184,8 @@ static StreamParams to_stream(const SpmmParams &p) {
   q.rowptr = p.rowptr; q.colind = p.colind; q.val = p.val; q.att = nullptr; q.perm = nullptr;
   q.X0 = p.X0; q.X1 = p.X1; q.n0 = p.n0; q.Y = p.Y; q.ldv = p.FV; q.H = 1; q.FVL = p.FV; q.S = 1;
   q.hub = p.hub;
+  q.n_peers = p.n_peers; q.peer_shift = p.peer_shift;
+  for (int i = 0; i < 8; ++i) q.peers[i] = p.peers[i];
   return q;
 }
 
@@ -240,7 +245,8 @@ static int dispatch_spmm(const SpmmParams &p, cudaStream_t s) {
 
 static int spmm_entry(const int32_t *rowptr, const int32_t *colind, const float *val, const float *X0,
                       int64_t n0, const float *X1, float *Y, int64_t n_rows, int64_t F,
-                      const cogdl_b200_hub_plan_t *plan, cogdl_b200_stream_t stream, const char *who) {
+                      const cogdl_b200_hub_plan_t *plan, cogdl_b200_stream_t stream, const char *who,
+                      const float *const *peers = nullptr, int n_peers = 0, int peer_shift = 0) {
   CB_REQUIRE(n_rows >= 0 && F >= 0, "%s: negative size (n_rows=%lld, F=%lld)", who, (long long)n_rows, (long long)F);
   if (n_rows == 0 || F == 0) return COGDL_B200_OK;
   CB_REQUIRE(rowptr && colind && X0 && Y, "%s: null pointer", who);
@@ -250,6 +256,15 @@ static int spmm_entry(const int32_t *rowptr, const int32_t *colind, const float 
   SpmmParams p;
   p.rowptr = rowptr; p.colind = colind; p.val = val; p.X0 = X0; p.X1 = X1 ? X1 : X0; p.n0 = n0;
   p.Y = Y; p.n_rows = n_rows; p.hub = hub_view(plan);
+  p.n_peers = n_peers; p.peer_shift = peer_shift;
+  bool peers_aligned = true;
+  for (int i = 0; i < 8; ++i) {
+    p.peers[i] = (i < n_peers) ? peers[i] : nullptr;
+    peers_aligned = peers_aligned && aligned16(p.peers[i]);
+  }
+  if (n_peers > 0)
+    CB_REQUIRE(p.hub.n_segs > 0 && F % 4 == 0 && F <= 512 && peers_aligned && aligned16(X0) && aligned16(Y),
+               "%s: the peer form needs a plan with segments, F %% 4 == 0, F <= 512 and 16-byte aligned buffers", who);
   const bool vec = (F % 4 == 0) && aligned16(X0) && aligned16(p.X1) && aligned16(Y) &&
                    (p.hub.n_chunks == 0 || aligned16(p.hub.partials));
   if (vec) {
@@ -398,4 +413,16 @@ extern "C" int cogdl_b200_spmm_csr_f16(const int32_t *rowptr, const int32_t *col
   }
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;
+}
+
+extern "C" int cogdl_b200_spmm_csr_f32_peers(const int32_t *rowptr, const int32_t *colind, const float *val,
+                                             const float *X_local, int64_t n_local, const float *const *peer_ptrs,
+                                             int32_t n_peers, int32_t owner_shift, float *Y, int64_t n_rows,
+                                             int64_t F, const cogdl_b200_hub_plan_t *plan,
+                                             cogdl_b200_stream_t stream) {
+  CB_REQUIRE(peer_ptrs && n_peers >= 1 && n_peers <= 8, "cogdl_b200_spmm_csr_f32_peers: need 1..8 peer pointers");
+  CB_REQUIRE(owner_shift >= 1 && owner_shift <= 28 && n_local >= 0, "cogdl_b200_spmm_csr_f32_peers: bad owner_shift / n_local");
+  for (int i = 0; i < n_peers; ++i) CB_REQUIRE(peer_ptrs[i], "cogdl_b200_spmm_csr_f32_peers: null peer pointer %d", i);
+  return spmm_entry(rowptr, colind, val, X_local, n_local, nullptr, Y, n_rows, F, plan, stream,
+                    "cogdl_b200_spmm_csr_f32_peers", peer_ptrs, n_peers, owner_shift);
 }

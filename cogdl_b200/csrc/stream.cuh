@@ -28,6 +28,12 @@ struct StreamParams {
   const float *X0;
   const float *X1;    // second source (two-source form), rows >= n0
   int64_t n0;
+  // peer form (node-range partition, fused NVLink gather): a column c >= n0 encodes
+  // (owner << peer_shift | row inside the owner's shard) after subtracting n0; peers[owner] is that
+  // rank's feature shard mapped into this process (symmetric memory / CUDA IPC).
+  const float *peers[8];
+  int n_peers;
+  int peer_shift;
   float *Y;
   int ldv;            // dense row length in VecT units
   int H;              // MODE 2: heads
@@ -37,6 +43,7 @@ struct StreamParams {
 };
 
 enum { MODE_UNWEIGHTED = 0, MODE_WEIGHTED = 1, MODE_MULTIHEAD = 2 };
+enum { SRC_ONE = 0, SRC_TWO = 1, SRC_PEERS = 2 };
 
 template <typename VecT> __device__ __forceinline__ VecT sk_zero();
 template <> __device__ __forceinline__ float4 sk_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -46,7 +53,7 @@ __device__ __forceinline__ void sk_add(float4 &a, const float4 &b) { add_rn(a, b
 
 // Stream the edge range [e, e_end).  ROWS: flush at row ends (segment); otherwise accumulate the
 // whole range into acc (hub chunk).
-template <typename VecT, int NV, int MODE, bool HAS_PERM, bool TWO_SRC, int U, bool ROWS, bool PREFETCH, bool HINT>
+template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, bool ROWS, bool PREFETCH, bool HINT>
 __device__ __forceinline__ void stream_range(const StreamParams &p, int e, const int e_end, const int cv,
                                              const bool (&colok)[NV], const int head, const int lane,
                                              VecT (&acc)[NV]) {
@@ -91,7 +98,16 @@ __device__ __forceinline__ void stream_range(const StreamParams &p, int e, const
         const int cj = __shfl_sync(FULL, c, j + u);
         const int pj = (MODE == MODE_MULTIHEAD) ? __shfl_sync(FULL, pe, j + u) : 0;
         if (full || j + u < cnt) {
-          const VecT *xp = (!TWO_SRC || cj < p.n0) ? X0 + (int64_t)cj * p.ldv : X1 + ((int64_t)cj - p.n0) * p.ldv;
+          const VecT *xp;
+          if (SRC == SRC_ONE || cj < p.n0) {
+            xp = X0 + (int64_t)cj * p.ldv;
+          } else if (SRC == SRC_TWO) {
+            xp = X1 + ((int64_t)cj - p.n0) * p.ldv;
+          } else {  // remote row: read it from the owner's HBM over NVLink
+            const unsigned r = (unsigned)(cj - (int)p.n0);
+            xp = reinterpret_cast<const VecT *>(p.peers[r >> p.peer_shift]) + cv +
+                 (int64_t)(r & ((1u << p.peer_shift) - 1u)) * p.ldv;
+          }
 #pragma unroll
           for (int k = 0; k < NV; ++k)
             if (colok[k]) x[u][k] = HINT ? ld_gather_hint(xp + k * 32, pol) : ld_gather(xp + k * 32);
@@ -124,7 +140,7 @@ __device__ __forceinline__ void stream_range(const StreamParams &p, int e, const
   }
 }
 
-template <typename VecT, int NV, int MODE, bool HAS_PERM, bool TWO_SRC, int U, int MINB, bool PREFETCH, bool HINT>
+template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, int MINB, bool PREFETCH, bool HINT>
 __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p) {
   constexpr int TILE = 32 * NV;
   const int lane = threadIdx.x & 31;
@@ -148,7 +164,7 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
 #pragma unroll
       for (int k = 0; k < NV; ++k) { colok[k] = (cv + k * 32) < p.ldv; acc[k] = sk_zero<VecT>(); }
       const int head = (MODE == MODE_MULTIHEAD && colok[0]) ? cv / p.FVL : 0;
-      stream_range<VecT, NV, MODE, HAS_PERM, TWO_SRC, U, false, PREFETCH, HINT>(p, w.lb, w.hb, cv, colok, head, lane, acc);
+      stream_range<VecT, NV, MODE, HAS_PERM, SRC, U, false, PREFETCH, HINT>(p, w.lb, w.hb, cv, colok, head, lane, acc);
 #pragma unroll
       for (int k = 0; k < NV; ++k)
         if (colok[k]) st_cg(P + (int64_t)w.slot * p.ldv + cv + k * 32, acc[k]);
@@ -192,7 +208,7 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
         }
       }
     }
-    stream_range<VecT, NV, MODE, HAS_PERM, TWO_SRC, U, true, PREFETCH, HINT>(p, e_begin, e_end, cv, colok, head, lane, acc);
+    stream_range<VecT, NV, MODE, HAS_PERM, SRC, U, true, PREFETCH, HINT>(p, e_begin, e_end, cv, colok, head, lane, acc);
   }
 }
 
@@ -204,20 +220,22 @@ static int launch_stream(const StreamParams &p, int mode, cudaStream_t stream) {
   if (blocks == 0) return COGDL_B200_OK;
   if (blocks > 0x7fffffffLL) return set_error(COGDL_B200_EINVAL, "stream kernel: problem too large for one launch");
   const unsigned g = (unsigned)blocks;
-  const bool two = p.n0 != INT64_MAX;
+  const int src = p.n_peers > 0 ? SRC_PEERS : (p.n0 != INT64_MAX ? SRC_TWO : SRC_ONE);
   if (mode == MODE_MULTIHEAD) {
     if constexpr (NV == 1) {
-      if (p.perm) stream_kernel<VecT, 1, MODE_MULTIHEAD, true, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-      else stream_kernel<VecT, 1, MODE_MULTIHEAD, false, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+      if (p.perm) stream_kernel<VecT, 1, MODE_MULTIHEAD, true, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+      else stream_kernel<VecT, 1, MODE_MULTIHEAD, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
     } else {
       return set_error(COGDL_B200_EINVAL, "stream kernel: multi-head form needs NV == 1");
     }
   } else if (mode == MODE_WEIGHTED) {
-    if (two) stream_kernel<VecT, NV, MODE_WEIGHTED, false, true, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-    else stream_kernel<VecT, NV, MODE_WEIGHTED, false, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    if (src == SRC_PEERS) stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_PEERS, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    else if (src == SRC_TWO) stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_TWO, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    else stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
   } else {
-    if (two) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, true, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-    else stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, false, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    if (src == SRC_PEERS) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_PEERS, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    else if (src == SRC_TWO) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_TWO, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    else stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
   }
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;

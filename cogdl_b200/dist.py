@@ -61,6 +61,16 @@ class LocalPartition:
         owner = torch.searchsorted(bt, self.halo, right=True) - 1       # owner rank of every halo row
         self.recv_counts = torch.bincount(owner, minlength=world).tolist()   # rows I receive from each rank
         self.halo_owner_local = self.halo - bt[owner]                   # row index inside the owner's shard
+        # peer encoding (fused NVLink gather): remote column -> n_local + (owner << shift | row in owner's shard)
+        max_rows = max(bounds[k + 1] - bounds[k] for k in range(world))
+        self.peer_shift = max(1, int(max_rows - 1).bit_length())
+        if self.n_local + (world << self.peer_shift) >= 2**31:
+            self.col_peer = None      # does not fit int32: only the halo form is available
+        else:
+            rem_owner = torch.searchsorted(bt, remote, right=True) - 1
+            col_peer = col_local.clone()
+            col_peer[~is_local] = self.n_local + (rem_owner << self.peer_shift) + (remote - bt[rem_owner])
+            self.col_peer = col_peer
 
 
 def exchange_index_lists(part, group=None, comm_device=None):
@@ -103,29 +113,85 @@ def _all_to_all(out, inp, out_splits, in_splits, group=None):
 
 
 class PartitionedSpMM:
-    """Per-rank state + the step: y_local = spmm(x_local) with the halo exchange inside."""
+    """Per-rank state + the step  y_local = A_local @ X  of the node-range partitioned SpMM.
 
-    def __init__(self, part: LocalPartition, device, group=None, global_nnz=None, description=""):
+    mode "p2p"  (default on CUDA): feature shards live in torch symmetric memory; the SpMM kernel
+                reads remote rows straight from the owner's HBM over NVLink
+                (cogdl_b200_spmm_csr_f32_peers) -- gather and compute are ONE kernel.
+    mode "nccl": pack (gather kernel) -> all_to_all_single -> two-source SpMM on [X_local ; X_halo].
+    """
+
+    def __init__(self, part: LocalPartition, device, group=None, global_nnz=None, description="", mode=None):
         self.part, self.device, self.group = part, device, group
         self.n_local, self.n_halo, self.nnz_local = part.n_local, part.n_halo, part.nnz_local
-        comm_dev = device if dist.get_backend(group) == "nccl" else None
+        self.global_nnz = global_nnz
+        self._desc = description
+        self.world = part.world
+        nccl = dist.get_backend(group) == "nccl"
+        if mode is None:
+            mode = "p2p" if (device.type == "cuda" and nccl and part.col_peer is not None) else "nccl"
+        self.mode = mode
+        self.x_local = None
+        self._symm = None
+        if mode == "p2p":
+            self.exchange = "fused: remote rows read from peer HBM inside the SpMM kernel (symmetric memory, NVLink P2P)"
+            self.st = CSRStructure.from_int64(part.row_ptr.to(device), part.col_peer.to(device),
+                                              n_cols=part.n_local)
+            self.st.plan
+            self.val = None if part.val is None else part.val.to(device).float().contiguous()
+            rows = torch.tensor([part.n_local], device=device, dtype=torch.int64)
+            dist.all_reduce(rows, op=dist.ReduceOp.MAX, group=group)
+            self._symm_rows = int(rows)
+            return
+        comm_dev = device if nccl else None
         self.send_index, self.send_counts = exchange_index_lists(part, group, comm_dev)
         self.recv_counts = part.recv_counts
-        self.global_nnz = global_nnz
-        self.exchange = "NCCL all_to_all_single" if dist.get_backend(group) == "nccl" else "p2p"
-        self._desc = description
+        self.exchange = "NCCL all_to_all_single of packed halo rows" if nccl else "p2p isend/irecv (gloo)"
         if device.type == "cuda":
             self.st = CSRStructure.from_int64(part.row_ptr.to(device), part.col.to(device),
                                               n_cols=part.n_local + part.n_halo)
             self.st.plan
             self.val = None if part.val is None else part.val.to(device).float().contiguous()
             self.send_index32 = self.send_index.to(device).to(torch.int32).contiguous()
-        self.x_local = None
 
     def describe(self):
         return self._desc
 
-    # -- the three stages, separately callable (tests / profiling)
+    # ------------------------------------------------------------------ p2p form
+    def features(self, F):
+        """The local feature shard [n_local, F] inside symmetric memory (write X here; peers read it)."""
+        if self._symm is None or self._symm[0].shape[1] != F:
+            import ctypes
+
+            import torch.distributed._symmetric_memory as symm
+
+            buf = symm.empty((self._symm_rows, F), dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            self._symm = (buf, hdl, ptrs)
+        return self._symm[0][: self.n_local]
+
+    def spmm_p2p(self):
+        """Y_local from the features currently in the symmetric shards (barrier, then ONE kernel)."""
+        import ctypes
+
+        from . import _cabi
+        from .structure import _ptr, _stream
+
+        buf, hdl, ptrs = self._symm
+        F = buf.shape[1]
+        hdl.barrier()   # every rank's shard is written before anyone gathers from it
+        dev = self.device
+        with torch.cuda.device(dev):
+            y = torch.empty((self.n_local, F), dtype=torch.float32, device=dev)
+            plan, keep = self.st.plan_struct(self.st.plan.n_chunks * F * 4)
+            _cabi.call("cogdl_b200_spmm_csr_f32_peers", _ptr(self.st.rowptr), _ptr(self.st.colind), _ptr(self.val),
+                       _ptr(buf), self.n_local, ctypes.cast(ptrs, ctypes.c_void_p), self.world, self.part.peer_shift,
+                       _ptr(y), self.n_local, F, plan, _stream(dev))
+            del keep
+        return y
+
+    # ------------------------------------------------------------------ nccl (halo) form: three stages
     def pack(self, x_local):
         if x_local.is_cuda:
             from .operators._raw import gather_rows_raw
@@ -144,21 +210,31 @@ class PartitionedSpMM:
 
         return spmm_2src_raw(self.st, self.val, x_local, x_halo)
 
+    # ------------------------------------------------------------------ the step
     def spmm(self, x_local):
+        if self.mode == "p2p":
+            shard = self.features(x_local.shape[1])
+            if x_local.data_ptr() != shard.data_ptr():
+                shard.copy_(x_local)        # callers that keep X in features() skip this copy
+            return self.spmm_p2p()
         F = x_local.shape[1]
         halo = self.exchange_rows(self.pack(x_local), F)
         return self.local_spmm(x_local, halo)
 
     def last_kernel_seconds(self, step, torch_mod, iters=5):
-        """Mean duration of the local two-source SpMM kernel alone (CUDA events), for the roofline."""
-        F = self.x_local.shape[1]
-        halo = self.exchange_rows(self.pack(self.x_local), F)
+        """Mean duration of the SpMM kernel alone (CUDA events, max over ranks), for the roofline."""
+        if self.mode == "p2p":
+            fn = self.spmm_p2p
+        else:
+            F = self.x_local.shape[1]
+            halo = self.exchange_rows(self.pack(self.x_local), F)
+            fn = lambda: self.local_spmm(self.x_local, halo)
         for _ in range(2):
-            self.local_spmm(self.x_local, halo)
+            fn()
         a, b = torch_mod.cuda.Event(enable_timing=True), torch_mod.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(iters):
-            self.local_spmm(self.x_local, halo)
+            fn()
         b.record()
         torch_mod.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b) / iters / 1e3], device=self.device, dtype=torch.float64)
@@ -166,14 +242,14 @@ class PartitionedSpMM:
         return float(t)
 
 
-def partition_global_csr(row_ptr, col, val, rank, world, device, group=None):
+def partition_global_csr(row_ptr, col, val, rank, world, device, group=None, mode=None):
     """Slice a (replicated, host or device) global CSR into this rank's LocalPartition."""
     bounds = balanced_row_ranges(row_ptr, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     e0, e1 = int(row_ptr[lo]), int(row_ptr[hi])
     part = LocalPartition(rank, world, bounds, (row_ptr[lo:hi + 1] - e0).clone(), col[e0:e1].clone(),
                           None if val is None else val[e0:e1].clone())
-    return PartitionedSpMM(part, device, group, global_nnz=int(row_ptr[-1]))
+    return PartitionedSpMM(part, device, group, global_nnz=int(row_ptr[-1]), mode=mode)
 
 
 # papers100M-shaped graph, 1/8 of it per GPU (BASELINE configs[4]): fixed per-GPU work => weak scaling
@@ -182,7 +258,7 @@ PAPERS_EDGES_PER_GPU = synth.SHAPES["papers100M"][1] // 8     # 201 960 734
 
 
 def synthetic_partition(rank, world, device, seed=0, rows=PAPERS_ROWS_PER_GPU, edges=PAPERS_EDGES_PER_GPU,
-                        beta=0.05, hidden=128, group=None):
+                        beta=0.05, hidden=128, group=None, mode=None):
     """Generate this rank's shard directly on its GPU: power-law degrees inside the shard, a column is
     uniform over the WHOLE graph with probability beta (remote with prob. beta*(P-1)/P) and uniform
     inside the own range otherwise (the locality-controlled generator of SURVEY 8d)."""
@@ -207,6 +283,11 @@ def synthetic_partition(rank, world, device, seed=0, rows=PAPERS_ROWS_PER_GPU, e
     desc = (f"unweighted spmm hidden={hidden} (fp32), papers100M-shaped power-law CSR partitioned by node range: "
             f"{rows} rows + {edges} edges per GPU x {world} GPUs (= {n_total} nodes, {edges * world} edges), "
             f"columns remote-eligible with prob beta={beta}, seed {seed} [BASELINE configs[4] shape, 1/8 of papers100M per GPU]")
-    ps = PartitionedSpMM(part, device, group, global_nnz=edges * world, description=desc)
-    ps.x_local = torch.randn(rows, hidden, device=device, generator=torch.Generator(device=device).manual_seed(seed + rank))
+    ps = PartitionedSpMM(part, device, group, global_nnz=edges * world, description=desc, mode=mode)
+    gen = torch.Generator(device=device).manual_seed(seed + rank)
+    if ps.mode == "p2p":
+        ps.x_local = ps.features(hidden)          # X lives in the symmetric shard: no copy per step
+        ps.x_local.normal_(generator=gen)
+    else:
+        ps.x_local = torch.randn(rows, hidden, device=device, generator=gen)
     return ps

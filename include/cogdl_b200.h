@@ -135,6 +135,19 @@ COGDL_B200_API int cogdl_b200_spmm_csr_f32_2src(const int32_t *rowptr, const int
                                  int64_t n_rows, int64_t F, const cogdl_b200_hub_plan_t *plan,
                                  cogdl_b200_stream_t stream);
 
+/* Peer form of the partitioned SpMM: the gather over remote feature rows is fused into the kernel.
+ * A column c < n_local reads X_local[c]; a column c >= n_local encodes r = c - n_local with
+ * owner = r >> owner_shift and row = r & ((1 << owner_shift) - 1), and is read DIRECTLY from
+ * peer_ptrs[owner] -- that rank's feature shard mapped into this process (symmetric memory /
+ * CUDA IPC), i.e. ld.global over NVLink 5 / NVSwitch inside the SpMM kernel: no pack kernel, no
+ * all-to-all, no halo buffer.  peer_ptrs is a HOST array of n_peers (<= 8) device pointers.
+ * Needs a hub plan with segments (row-stream kernel), F % 4 == 0, F <= 512.  The caller orders
+ * the peers' writes to their shards before this call (barrier) -- see cogdl_b200/dist.py. */
+COGDL_B200_API int cogdl_b200_spmm_csr_f32_peers(const int32_t *rowptr, const int32_t *colind, const float *val,
+                                  const float *X_local, int64_t n_local, const float *const *peer_ptrs,
+                                  int32_t n_peers, int32_t owner_shift, float *Y, int64_t n_rows, int64_t F,
+                                  const cogdl_b200_hub_plan_t *plan, cogdl_b200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * CSR SDDMM   out[p] = < D1[row(p),:], D2[colind[p],:] >
  * Replaces  sddmm.csr_sddmm(rowptr, colind, D1, D2)   cogdl/operators/spmm/sddmm.cpp:47-70

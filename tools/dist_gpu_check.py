@@ -24,18 +24,23 @@ def main():
     rp, col = synth.powerlaw_csr(n, e, seed=7, locality=(world, 0.1))
     val = torch.rand(col.numel(), generator=torch.Generator().manual_seed(1))
     X = torch.randn(n, F, generator=torch.Generator().manual_seed(2))
-    ps = cdist.partition_global_csr(rp, col, val, rank, world, dev)
-    lo, hi = ps.part.lo, ps.part.hi
-    y = ps.spmm(X[lo:hi].to(dev).contiguous())
-    torch.cuda.synchronize()
-    ref = oracle.spmm_csr(rp.numpy(), col.numpy(), val.numpy(), X.numpy())[lo:hi]
-    got = y.cpu().numpy()
-    err = float(np.abs(got - ref).max() / np.abs(ref).max())
-    deg = np.diff(rp.numpy())[lo:hi]
-    exact = np.array_equal(got[deg <= ps.st.chunk_edges], ref[deg <= ps.st.chunk_edges])
-    ok = torch.tensor([1 if (err <= 1e-5 and exact) else 0], device=dev)
+    full = oracle.spmm_csr(rp.numpy(), col.numpy(), val.numpy(), X.numpy())
+    ok = torch.tensor([1], device=dev)
+    for mode in ("nccl", "p2p"):
+        ps = cdist.partition_global_csr(rp, col, val, rank, world, dev, mode=mode)
+        lo, hi = ps.part.lo, ps.part.hi
+        y = ps.spmm(X[lo:hi].to(dev).contiguous())
+        torch.cuda.synchronize()
+        ref = full[lo:hi]
+        got = y.cpu().numpy()
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        deg = np.diff(rp.numpy())[lo:hi]
+        exact = np.array_equal(got[deg <= ps.st.chunk_edges], ref[deg <= ps.st.chunk_edges])
+        if not (err <= 1e-5 and exact):
+            ok.zero_()
+        print(f"[rank {rank}] mode={mode} rows [{lo},{hi}) halo {ps.n_halo} rel_err {err:.2e} unsplit_rows_bit_exact {exact}", flush=True)
+        dist.barrier()
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    print(f"[rank {rank}] rows [{lo},{hi}) halo {ps.n_halo} rel_err {err:.2e} unsplit_rows_bit_exact {exact}", flush=True)
     if rank == 0:
         print("DIST_CHECK", "PASS" if int(ok) == 1 else "FAIL", flush=True)
     dist.barrier()
