@@ -203,7 +203,9 @@ static int launch_spmm_stream(const SpmmParams &p, cudaStream_t stream) {
       case 6: return launch_stream<VecT, 1, 8, 3>(q, mode, stream);
       case 1: return launch_stream<VecT, 1, 8, 4>(q, mode, stream);
       case 8: return launch_stream<VecT, 1, 4, 5, false, true>(q, mode, stream);   // + L2 evict_last hint on X
-      case 9: return launch_stream<VecT, 1, 8, 4, false, true>(q, mode, stream);
+      case 10: return launch_stream<VecT, 1, 4, 4, false>(q, mode, stream);
+      case 11: return launch_stream<VecT, 1, 8, 3, false>(q, mode, stream);
+      case 12: return launch_stream<VecT, 1, 6, 4, false>(q, mode, stream);
       // U=4, 48 registers (40 warps/SM), no slab prefetch: fastest measured (profiles/r01d_tune_stream_v2.txt)
       default: return launch_stream<VecT, 1, 4, 5, false>(q, mode, stream);
     }

@@ -71,7 +71,7 @@ if __name__ == "__main__":
     run("arxiv", 7, 128, 64)
     os.environ.pop("TUNE_EXTRA")
     for shape in ("arxiv", "products"):
-        for variant in (7, 8, 5, 9):
+        for variant in (7, 10, 12, 11, 5):
             run(shape, variant, 128, 64)
-        run(shape, 8, 128, 128)
-        run(shape, 7, 128, 128)
+        run(shape, 10, 128, 128)
+        run(shape, 10, 96, 48)
