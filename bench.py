@@ -432,7 +432,7 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the SpMM kernel at the N=1 workload, from the
 # committed `ncu --set full` capture (profiles/); None until a capture exists.
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 308029184  # 237.96 MB read + 70.07 MB write, profiles/r01f_spmm_stream_ncu_summary.txt
 
 
 def main():

@@ -36,6 +36,7 @@ class HubPlanStruct(ctypes.Structure):
         ("n_segs", ctypes.c_int32),
         ("segs", ctypes.c_void_p),
         ("edge_row", ctypes.c_void_p),
+        ("hub_degrees_host", ctypes.c_void_p),
     ]
 
 

@@ -92,6 +92,16 @@ class HubPlan:
                 _cabi.call("cogdl_b200_hub_plan_fill", _ptr(rowptr32), n_rows, self.chunk_edges,
                            self.seg_cost if self.segs is not None else 0, _ptr(counts), _ptr(self.hub_rows),
                            _ptr(self.chunks), _ptr(self.segs), _stream(dev))
+            # hub rows by descending degree + a host copy of the degrees (row-tiered ops size their
+            # block / cluster launches from it); the chunk table refers to rows, not to list positions
+            self.hub_degrees_host = None
+            if n_hub > 0:
+                hr = self.hub_rows[:n_hub].long()
+                deg = (rowptr32[hr + 1] - rowptr32[hr]).to(torch.int32)
+                order = torch.argsort(deg, descending=True, stable=True)
+                self.hub_rows[:n_hub] = self.hub_rows[:n_hub][order]
+                self._hub_deg_np = deg[order].cpu().numpy().astype("int32")
+                self.hub_degrees_host = self._hub_deg_np.ctypes.data
 
     def struct(self, partial_bytes=0):
         """ctypes struct for one call; partial scratch comes from torch's caching allocator.
@@ -104,6 +114,7 @@ class HubPlan:
         s.chunks = self.chunks.data_ptr()
         s.counters = self.counters.data_ptr()
         s.n_empty_rows = self.n_empty_rows
+        s.hub_degrees_host = self.hub_degrees_host
         if self.segs is not None:
             s.seg_cost, s.n_segs = self.seg_cost, self.n_segs
             s.segs, s.edge_row = self.segs.data_ptr(), self.edge_row.data_ptr()

@@ -91,6 +91,11 @@ typedef struct cogdl_b200_hub_plan {
   int32_t n_segs;
   const int32_t *segs;     /* [2*n_segs] (row_begin, row_end), any order */
   const int32_t *edge_row; /* [nnz] */
+  /* Optional: HOST array of the hub rows' degrees, in hub_rows order, sorted DESCENDING (the caller
+   * sorts hub_rows accordingly).  Lets row-tiered ops (edge softmax, GAT attention) launch exactly
+   * as many blocks / clusters as there are rows in a tier.  NULL => such ops treat every hub row
+   * with the per-warp tier. */
+  const int32_t *hub_degrees_host;
 } cogdl_b200_hub_plan_t;
 
 /* Pass 1: counts_dev[0..3] = #rows with degree > chunk_edges, #chunks, #empty rows, #segments

@@ -108,6 +108,42 @@ def test_spmm_two_source(dev):
     assert np.array_equal(y, ref)
 
 
+def test_spmm_peer_form_single_gpu(dev):
+    """The fused-gather kernel (cogdl_b200_spmm_csr_f32_peers) with the 'peers' being three separate
+    buffers on this GPU: checks the (owner << shift | row) column decoding and the per-owner base
+    pointers without needing NVLink (the multi-GPU run is tools/dist_gpu_check.py)."""
+    import ctypes
+
+    from cogdl_b200 import _cabi
+    from cogdl_b200.structure import _ptr, _stream
+
+    rp, ci, n_cols = case("two_hubs")
+    n = rp.shape[0] - 1
+    rng = np.random.default_rng(14)
+    F = 128
+    X = rng.standard_normal((n_cols, F)).astype(np.float32)
+    val = rng.random(ci.shape[0]).astype(np.float32)
+    ref = oracle.spmm_csr(rp, ci, val, X)
+    # shards: [0,400) local, [400,700) owner 1, [700,1000) owner 2 ; owner 0 = local buffer itself
+    bounds = [0, 400, 700, n_cols]
+    shift = 9
+    enc = ci.copy()
+    for o in (1, 2):
+        m = (ci >= bounds[o]) & (ci < bounds[o + 1])
+        enc[m] = bounds[1] + (o << shift) + (ci[m] - bounds[o])
+    shards = [T(X[bounds[o]:bounds[o + 1]], dev) for o in range(3)]
+    st = structure(rp, enc, n_cols, dev)
+    ptrs = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in shards])
+    y = torch.empty((n, F), device=dev)
+    plan, keep = st.plan_struct(st.plan.n_chunks * F * 4)
+    _cabi.call("cogdl_b200_spmm_csr_f32_peers", _ptr(st.rowptr), _ptr(st.colind), _ptr(T(val, dev)), _ptr(shards[0]),
+               bounds[1], ctypes.cast(ptrs, ctypes.c_void_p), 3, shift, _ptr(y), n, F, plan, _stream(dev))
+    torch.cuda.synchronize()
+    got = y.cpu().numpy()
+    unsplit = np.diff(rp) <= st.chunk_edges
+    assert np.array_equal(got[unsplit], ref[unsplit]) and rel(got, ref) <= TOL
+
+
 # ------------------------------------------------------------------------------------ SDDMM
 @pytest.mark.parametrize("name", ["tiny", "ragged", "hub", "rect", "empty_graph"])
 @pytest.mark.parametrize("F", [128, 16, 40, 7, 256, 1, 600])

@@ -70,8 +70,4 @@ if __name__ == "__main__":
     os.environ["TUNE_EXTRA"] = "1"
     run("arxiv", 7, 128, 64)
     os.environ.pop("TUNE_EXTRA")
-    for shape in ("arxiv", "products"):
-        for variant in (7, 10, 12, 11, 5):
-            run(shape, variant, 128, 64)
-        run(shape, 10, 128, 128)
-        run(shape, 10, 96, 48)
+    run("products", 7, 128, 64)
