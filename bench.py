@@ -289,6 +289,42 @@ def extras(torch, flush, steps=10):
     bench("C3_mhspmm_H8_F128", lambda: mhspmm_raw(st, att, h), mh_bytes, nnz)
     hl, hr = torch.randn(n, H, device=dev), torch.randn(n, H, device=dev)
     bench("C3_fused_gat_H8_F128", lambda: gat_fwd_raw(st, hl, hr, h, 0.2, False), mh_bytes, nnz)
+    # ---- secondary: whole training steps of the three config models on the arxiv shape (cuBLAS GEMMs +
+    # our sparse kernels + autograd: forward, backward, SGD), informational
+    def train_step_ms(model, graph, out_dim, reps=5):
+        import torch.nn.functional as Fn
+
+        opt = torch.optim.SGD(model.parameters(), lr=0.01)
+        y = torch.randint(0, out_dim, (n,), device=dev)
+        ts = []
+        for i in range(reps + 2):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            opt.zero_grad(set_to_none=True)
+            loss = Fn.cross_entropy(model(graph), y)
+            loss.backward()
+            opt.step()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    try:
+        from cogdl_b200.layers import GCN, GAT, SAGE
+
+        g.x = torch.randn(n, 128, device=dev)
+        res["C2_gcn2_train_step"] = {"ms": train_step_ms(GCN(128, 128, 40, dropout=0.0).to(dev), g, 40),
+                                     "what": "2-layer GCN hidden=128, fwd+bwd+SGD, arxiv shape"}
+        g2 = cogdl_b200.Graph(x=g.x, row_ptr=rp, col=col, num_nodes=n).to(dev)
+        res["C3_gat2_train_step"] = {"ms": train_step_ms(GAT(128, 16, 40, nhead=8, last_nhead=1).to(dev), g2, 40),
+                                     "what": "2-layer GAT 8 heads x 16, fwd+bwd+SGD, arxiv shape"}
+        res["C4_sage_max2_train_step"] = {"ms": train_step_ms(SAGE(128, 128, 40, aggr="max").to(dev), g2, 40),
+                                          "what": "2-layer GraphSAGE aggr=max hidden=128, fwd+bwd+SGD, arxiv shape"}
+        del g2
+    except Exception as ex:  # noqa: BLE001  (secondary numbers must not take the headline down)
+        res["train_steps_error"] = f"{type(ex).__name__}: {ex}"
     del h, att, logits, x128, x40, g, st
     n, e = synth.SHAPES["products"]
     rp, col = synth.powerlaw_csr(n, e, seed=0, device=dev, self_loops=False)
@@ -338,7 +374,6 @@ def run_ours(args):
         l0 = _cabi.launch_count()
         sampler.start()
         ms = time_steps(step, args.steps, args.warmup, flush, torch, False)
-        clocks = sampler.stop()
         launches_dev = _cabi.launch_count() - l0
         # ---- end to end: pinned host X -> device, spmm through the public API, Y -> pinned host
         x_pin = x_host.pin_memory()
@@ -352,6 +387,7 @@ def run_ours(args):
 
         l1 = _cabi.launch_count()
         ms_e2e = time_steps(e2e_step, args.steps, args.warmup, flush, torch, False)
+        clocks = sampler.stop()      # sampled across both timed regions
         launches = launches_dev + (_cabi.launch_count() - l1)
         total_units = nnz
         algo, bmin = spmm_bytes(n, nnz, F_HIDDEN)

@@ -41,6 +41,17 @@ def _worker(rank, world, port, out_dir):
         halo = ps.exchange_rows(ps.pack(x_local), F)
         assert torch.equal(halo, X[part.halo])                   # every fetched row is the right row
         assert part.n_halo > 0 and int(part.col.max()) < part.n_local + part.n_halo
+        # peer encoding used by the fused NVLink gather: n_local + (owner << shift | row in owner's shard)
+        cp = part.col_peer
+        e0, e1 = int(rp[lo]), int(rp[hi])
+        glob = col[e0:e1]
+        local = cp < part.n_local
+        assert torch.equal(cp[local] + lo, glob[local])
+        r = cp[~local] - part.n_local
+        owner, idx = r >> part.peer_shift, r & ((1 << part.peer_shift) - 1)
+        bt = torch.tensor(part.bounds)
+        assert torch.equal(bt[owner] + idx, glob[~local]) and bool((owner != rank).all())
+        assert bool((idx < (bt[owner + 1] - bt[owner])).all())
         y_local = oracle.spmm_csr(part.row_ptr.numpy(), part.col.numpy(), part.val.numpy(),
                                   torch.cat([x_local, halo]).numpy())
         y_global = oracle.spmm_csr(rp.numpy(), col.numpy(), val.numpy(), X.numpy())
