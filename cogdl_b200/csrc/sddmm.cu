@@ -16,6 +16,8 @@
 // lane (F >= 128).  Dot products are reduced with xor-shuffles inside the SUB lanes.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace cogdl_b200 {
 
 struct SddmmParams {
@@ -134,6 +136,97 @@ __global__ void __launch_bounds__(256) sddmm_kernel(const SddmmParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-stream form (plan with segments, F a multiple of 128 per head, float4 path): one warp per
+// (edge range, head) where the edge ranges are the plan's hub chunks and segments.  Outputs are per
+// edge, so chunks and segments are the same thing here: no flush, no partials.  Both operands are
+// gathered per edge -- the left one (D1 / grad row of the edge's OWN row, via edge_row) repeats for
+// consecutive edges of a row and is served by L1 -- so every batch has 2*U independent 512-byte
+// loads in flight and there is no per-row reload latency.
+// ------------------------------------------------------------------------------------------
+template <int NV, int U>
+__global__ void __launch_bounds__(256) sddmm_stream_kernel(const SddmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t item = wid / p.NSEG;
+  const int head = (int)(wid - item * p.NSEG);
+  int e, e_end, fixed_row = -1;
+  if (item < p.hub.n_chunks) {
+    const WorkItem w = decode_item(item, 0, p.rowptr, p.hub);
+    e = w.lb; e_end = w.hb; fixed_row = w.row;
+  } else {
+    const int64_t seg = item - p.hub.n_chunks;
+    if (seg >= p.hub.n_segs) return;
+    const int2 rr = __ldg(p.hub.segs + seg);
+    e = __ldg(p.rowptr + rr.x); e_end = __ldg(p.rowptr + rr.y);
+  }
+  const int64_t ld = (int64_t)p.NSEG * p.L;
+  const float4 *D1 = reinterpret_cast<const float4 *>(p.D1) + (int64_t)head * p.L + lane;
+  const float4 *D2 = reinterpret_cast<const float4 *>(p.D2) + (int64_t)head * p.L + lane;
+  for (; e < e_end; e += 32) {
+    const int cnt = min(32, e_end - e);
+    int c = 0, r = 0;
+    if (lane < cnt) {
+      c = ld_stream(p.colind + e + lane);
+      r = fixed_row >= 0 ? fixed_row : ld_stream(p.hub.edge_row + e + lane);
+    }
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += U) {
+      float4 a[U][NV], b[U][NV];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cj = __shfl_sync(FULL, c, j + u);
+        const int rj = __shfl_sync(FULL, r, j + u);
+        if (j + u < cnt) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            a[u][k] = __ldg(D1 + (int64_t)rj * ld + 32 * k);
+            b[u][k] = ld_gather(D2 + (int64_t)cj * ld + 32 * k);
+          }
+        }
+      }
+      float d[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        d[u] = 0.f;
+        if (j + u < cnt) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) d[u] += vdot(a[u][k], b[u][k]);
+        }
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) d[u] += __shfl_xor_sync(FULL, d[u], s);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lane == u && j + u < cnt) p.out[(int64_t)(e + j + u) * p.NSEG + head] = d[u];
+    }
+  }
+}
+
+static bool sddmm_stream_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("COGDL_B200_SDDMM_STREAM");
+    v = e ? atoi(e) : 0;   // measured on B200 (arxiv shape): 189 vs 175 us (F=128), 1377 vs 1317 us (H=8,F=128):
+                           // gathering both operands costs more LSU traffic than the row form saves -> off
+  }
+  return v != 0;
+}
+
+template <int NV>
+static int launch_sddmm_stream(const SddmmParams &p, cudaStream_t stream) {
+  const int64_t warps = ((int64_t)p.hub.n_chunks + p.hub.n_segs) * p.NSEG;
+  const int64_t blocks = ceil_div(warps * 32, 256);
+  if (blocks == 0) return COGDL_B200_OK;
+  if (blocks > 0x7fffffffLL) return set_error(COGDL_B200_EINVAL, "sddmm: problem too large for one launch");
+  sddmm_stream_kernel<NV, (NV == 1 ? 4 : 2)><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  CB_LAUNCH_CHECK();
+  return COGDL_B200_OK;
+}
+
 template <typename VecT, int GROUP, int SUB, int NV>
 static int launch_sddmm(const SddmmParams &p, cudaStream_t stream) {
   const int64_t items = (int64_t)p.hub.n_chunks + p.n_rows;
@@ -151,6 +244,12 @@ static int launch_sddmm(const SddmmParams &p, cudaStream_t stream) {
 template <typename VecT>
 static int dispatch_sddmm(const SddmmParams &p, cudaStream_t s) {
   const int L = p.L, H = p.NSEG;
+  if constexpr (sizeof(VecT) == 16) {
+    if (p.hub.n_segs > 0 && sddmm_stream_enabled()) {
+      if (L == 32) return launch_sddmm_stream<1>(p, s);
+      if (L == 64) return launch_sddmm_stream<2>(p, s);
+    }
+  }
   if (L > 128) return launch_sddmm<VecT, 32, 32, 0>(p, s);
   if (L > 64) return launch_sddmm<VecT, 32, 32, 4>(p, s);
   if (L > 32) return launch_sddmm<VecT, 32, 32, 2>(p, s);
