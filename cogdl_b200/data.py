@@ -25,7 +25,6 @@ def coo2csr_index(row, num_nodes):
     cogdl/operators/sample/sample.cpp:234-270, single-thread CPU even for CUDA graphs)."""
     row = row.long().contiguous()
     if row.is_cuda:
-        import ctypes
         from . import _cabi
         from .structure import _ptr, _stream
 

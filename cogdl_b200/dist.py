@@ -18,8 +18,6 @@ sums", north star) moves the same order of bytes -- (#distinct remote rows) * 4F
 needs the column-sliced matrix and an extra reduction pass, so the pull form is what is built.
 There is no all-reduce on the data path: a row's sum is completed by exactly one rank.
 """
-import math
-
 import torch
 import torch.distributed as dist
 

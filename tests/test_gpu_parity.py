@@ -298,6 +298,49 @@ def test_fused_gat_forward(dev, name, H, F):
     assert rel(att.cpu().numpy(), ref_att) <= TOL
 
 
+# ------------------------------------------------------------------------------------ hub plan invariants
+@pytest.mark.parametrize("name", ["ragged", "hub", "two_hubs", "tiny", "empty_graph"])
+@pytest.mark.parametrize("chunk,seg", [(64, 128), (256, 32), (8, 16)])
+def test_hub_plan_invariants(dev, name, chunk, seg):
+    """The plan is what every kernel's work decomposition rests on: hub chunks must tile exactly the
+    hub rows, segments must partition exactly the non-hub rows (in contiguous, hub-free runs), edge_row
+    must be the COO row array, the hub list must be sorted by descending degree."""
+    from cogdl_b200.structure import CSRStructure
+
+    rp, ci, n_cols = case(name)
+    n = rp.shape[0] - 1
+    deg = np.diff(rp)
+    st = CSRStructure(T(rp, dev), T(ci, dev), n_cols=n_cols, chunk_edges=chunk, seg_cost=seg)
+    pl = st.plan
+    hubs = np.nonzero(deg > chunk)[0]
+    assert pl.n_hub_rows == len(hubs) and pl.n_empty_rows == int((deg == 0).sum())
+    assert pl.n_chunks == int(np.ceil(deg[hubs] / chunk).sum())
+    hub_rows = pl.hub_rows[: pl.n_hub_rows].cpu().numpy()
+    assert sorted(hub_rows.tolist()) == hubs.tolist()
+    assert np.all(np.diff(deg[hub_rows]) <= 0)                       # descending degree
+    if pl.n_hub_rows:
+        assert np.array_equal(pl._hub_deg_np, deg[hub_rows].astype(np.int32))
+    chunks = pl.chunks[: 2 * pl.n_chunks].cpu().numpy().reshape(-1, 2)
+    for r in hubs:                                                   # a row's chunks: contiguous slots, one first_slot
+        mine = np.nonzero(chunks[:, 0] == r)[0]
+        assert len(mine) == -(-deg[r] // chunk)
+        assert np.array_equal(mine, np.arange(mine[0], mine[0] + len(mine))) and np.all(chunks[mine, 1] == mine[0])
+    if ci.shape[0] == 0:
+        return
+    assert pl.n_segs > 0
+    segs = pl.segs.cpu().numpy().reshape(-1, 2)
+    covered = np.zeros(n, np.int32)
+    for a, b in segs:
+        assert 0 <= a < b <= n
+        assert np.all(deg[a:b] <= chunk)                             # hub-free
+        covered[a:b] += 1
+        cost = int(rp[b] - rp[a]) + (b - a)
+        assert cost <= seg + chunk + 1                               # bounded work per warp
+    assert np.array_equal(covered, (deg <= chunk).astype(np.int32))  # every non-hub row exactly once
+    assert np.array_equal(pl.edge_row.cpu().numpy(), np.repeat(np.arange(n), deg).astype(np.int32))
+    assert int(pl.counters.abs().sum()) == 0
+
+
 # ------------------------------------------------------------------------------------ structure tools
 def test_coo2csr_index_device_bit_exact(dev):
     from cogdl_b200.data import coo2csr_index
