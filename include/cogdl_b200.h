@@ -6,8 +6,9 @@
  * exposes today through a pybind11/torch extension (THUDM/CogDL @ 281f4742; paths relative to
  * the CogDL tree).  Differences from the reference ABI, all deliberate:
  *   - plain C: raw device pointers + int64 sizes + an opaque stream handle, no torch types;
- *   - the caller owns every buffer (outputs included); nothing persistent is allocated here
- *     (the reference leaks a cusparseHandle and cudaMalloc's per call, spmm_kernel.cu:517-531);
+ *   - the caller owns every buffer (outputs included); no device memory is allocated here (the
+ *     reference leaks a cusparseHandle and cudaMalloc's per call, spmm_kernel.cu:517-531); the only
+ *     persistent objects are one side stream + two events per device used by the edge-softmax tiers;
  *   - work is enqueued on the caller's stream (the reference uses the legacy default stream);
  *   - errors are returned (0 = ok, <0 = COGDL_B200_E*), text via cogdl_b200_last_error();
  *     the reference `assert`s / exit(1)s (spmm.cpp:28-39, computeUtil.h:13-27);
