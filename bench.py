@@ -396,7 +396,8 @@ def run_ours(args):
     else:
         from cogdl_b200 import dist as cdist
 
-        part = cdist.synthetic_partition(rank, world, dev, seed=0, mode=os.environ.get("COGDL_B200_DIST_MODE"))
+        part = cdist.synthetic_partition(rank, world, dev, seed=0, mode=os.environ.get("COGDL_B200_DIST_MODE"),
+                                         beta=float(os.environ.get("COGDL_B200_DIST_BETA", "0.05")))
         workload = part.describe()
         x_dev = part.x_local                       # p2p mode: already inside the symmetric shard
         step = lambda: part.spmm(x_dev)
