@@ -49,6 +49,7 @@ SIGNATURES = {
     "cogdl_b200_last_error": (ctypes.c_char_p, []),
     "cogdl_b200_check_device": (ctypes.c_int, []),
     "cogdl_b200_launch_count": (_i64, []),
+    "cogdl_b200_last_kernel": (ctypes.c_char_p, []),
     "cogdl_b200_hub_plan_count": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "cogdl_b200_hub_plan_fill": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cogdl_b200_edge_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp]),
@@ -111,3 +112,7 @@ def call(name, *args):
 
 def launch_count():
     return int(load().cogdl_b200_launch_count())
+
+
+def last_kernel():
+    return load().cogdl_b200_last_kernel().decode("utf-8", "replace")

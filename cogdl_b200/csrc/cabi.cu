@@ -21,6 +21,14 @@ int set_error(int code, const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static thread_local char g_kernel[256] = {0};
+void note_kernel(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
+  va_end(ap);
+}
+
 int check_plan(const cogdl_b200_hub_plan_t *plan, int64_t need_partial_bytes) {
   if (!plan || plan->chunk_edges <= 0) return COGDL_B200_OK;
   if (plan->n_chunks < 0 || plan->n_hub_rows < 0)
@@ -116,6 +124,8 @@ extern "C" int cogdl_b200_abi_version(void) { return COGDL_B200_ABI_VERSION; }
 extern "C" const char *cogdl_b200_last_error(void) { return g_err; }
 
 extern "C" int64_t cogdl_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" const char *cogdl_b200_last_kernel(void) { return g_kernel; }
 
 extern "C" int cogdl_b200_check_device(void) {
   int dev = 0;

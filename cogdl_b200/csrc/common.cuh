@@ -14,6 +14,9 @@ namespace cogdl_b200 {
 // ------------------------------------------------------------------ host side
 int set_error(int code, const char *fmt, ...);
 void count_launch(int n = 1);
+// Records which kernel instantiation the last dispatching entry point on this thread chose
+// (cogdl_b200_last_kernel(); bench.py checks it against the profiled kernel's name).
+void note_kernel(const char *fmt, ...);
 
 #define CB_REQUIRE(cond, ...)                                             \
   do {                                                                    \

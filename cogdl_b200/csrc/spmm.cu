@@ -223,6 +223,8 @@ static int launch_spmm(const SpmmParams &p, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL)
     return set_error(COGDL_B200_EINVAL, "spmm: problem too large for one launch (blocks=%lld)", (long long)blocks);
   dim3 grid((unsigned)blocks);
+  note_kernel("cogdl_b200::spmm_kernel<%s,GROUP=%d,NV=%d,%s>", sizeof(VecT) == 16 ? "float4" : "float", GROUP, NV,
+              p.val ? "weighted" : "unweighted");
   if (p.val)
     spmm_kernel<VecT, GROUP, NV, true><<<grid, 256, 0, stream>>>(p);
   else
@@ -234,6 +236,9 @@ static int launch_spmm(const SpmmParams &p, cudaStream_t stream) {
 template <typename VecT>
 static int dispatch_spmm(const SpmmParams &p, cudaStream_t s) {
   const int fv = p.FV;
+  // peer form: only the row-stream kernel decodes (owner << shift | row) columns (SRC_PEERS); the
+  // sub-warp row kernel below would read them as X1[c - n0].  NV = 1 masks lanes >= fv.
+  if (p.n_peers > 0 && fv <= 32) return launch_spmm_stream<VecT, 1>(p, s);
   if (fv <= 1) return launch_spmm<VecT, 1, 1>(p, s);
   if (fv <= 2) return launch_spmm<VecT, 2, 1>(p, s);
   if (fv <= 4) return launch_spmm<VecT, 4, 1>(p, s);

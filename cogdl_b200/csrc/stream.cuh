@@ -221,6 +221,11 @@ static int launch_stream(const StreamParams &p, int mode, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL) return set_error(COGDL_B200_EINVAL, "stream kernel: problem too large for one launch");
   const unsigned g = (unsigned)blocks;
   const int src = p.n_peers > 0 ? SRC_PEERS : (p.n0 != INT64_MAX ? SRC_TWO : SRC_ONE);
+  note_kernel("cogdl_b200::stream_kernel<%s,NV=%d,%s%s,%s,U=%d,MINB=%d%s%s>", sizeof(VecT) == 16 ? "float4" : "float", NV,
+              mode == MODE_MULTIHEAD ? "multihead" : (mode == MODE_WEIGHTED ? "weighted" : "unweighted"),
+              (mode == MODE_MULTIHEAD && p.perm) ? "+perm" : "",
+              src == SRC_PEERS ? "SRC_PEERS" : (src == SRC_TWO ? "SRC_TWO" : "SRC_ONE"), U, MINB,
+              PREFETCH ? ",prefetch" : "", HINT ? ",l2hint" : "");
   if (mode == MODE_MULTIHEAD) {
     if constexpr (NV == 1) {
       if (p.perm) stream_kernel<VecT, 1, MODE_MULTIHEAD, true, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);

@@ -131,6 +131,7 @@ class PartitionedSpMM:
         self.mode = mode
         self.x_local = None
         self._symm = None
+        self._symm_by_F = {}
         if mode == "p2p":
             self.exchange = "fused: remote rows read from peer HBM inside the SpMM kernel (symmetric memory, NVLink P2P)"
             self.st = CSRStructure.from_int64(part.row_ptr.to(device), part.col_peer.to(device),
@@ -157,8 +158,12 @@ class PartitionedSpMM:
 
     # ------------------------------------------------------------------ p2p form
     def features(self, F):
-        """The local feature shard [n_local, F] inside symmetric memory (write X here; peers read it)."""
-        if self._symm is None or self._symm[0].shape[1] != F:
+        """The local feature shard [n_local, F] inside symmetric memory (write X here; peers read it).
+        One symmetric buffer per feature width, kept for the life of the object (a multi-layer model
+        alternates widths; re-allocating + re-rendezvousing while a slower peer's kernel still reads
+        the old shard would be a use-after-free across ranks)."""
+        ent = self._symm_by_F.get(F)
+        if ent is None:
             import ctypes
 
             import torch.distributed._symmetric_memory as symm
@@ -166,8 +171,16 @@ class PartitionedSpMM:
             buf = symm.empty((self._symm_rows, F), dtype=torch.float32, device=self.device)
             hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
             ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
-            self._symm = (buf, hdl, ptrs)
-        return self._symm[0][: self.n_local]
+            ent = self._symm_by_F[F] = (buf, hdl, ptrs)
+        self._symm = ent
+        return ent[0][: self.n_local]
+
+    def release(self):
+        """Barrier that must precede ANY write to a shard returned by features(): a faster rank may
+        only overwrite its shard once every peer's previous SpMM kernel has finished gathering from
+        it (write-after-read across ranks).  spmm(x) does this itself when it copies x in."""
+        if self._symm is not None:
+            self._symm[1].barrier(channel=1)
 
     def spmm_p2p(self):
         """Y_local from the features currently in the symmetric shards (barrier, then ONE kernel)."""
@@ -213,7 +226,8 @@ class PartitionedSpMM:
         if self.mode == "p2p":
             shard = self.features(x_local.shape[1])
             if x_local.data_ptr() != shard.data_ptr():
-                shard.copy_(x_local)        # callers that keep X in features() skip this copy
+                self.release()              # peers' previous kernels are done reading this shard
+                shard.copy_(x_local)        # callers that keep X in features() skip barrier + copy
             return self.spmm_p2p()
         F = x_local.shape[1]
         halo = self.exchange_rows(self.pack(x_local), F)
@@ -251,36 +265,19 @@ def partition_global_csr(row_ptr, col, val, rank, world, device, group=None, mod
 
 
 # papers100M-shaped graph, 1/8 of it per GPU (BASELINE configs[4]): fixed per-GPU work => weak scaling
-PAPERS_ROWS_PER_GPU = synth.SHAPES["papers100M"][0] // 8      # 13 882 494
-PAPERS_EDGES_PER_GPU = synth.SHAPES["papers100M"][1] // 8     # 201 960 734
+PAPERS_ROWS_PER_GPU = synth.PAPERS_ROWS_PER_GPU
+PAPERS_EDGES_PER_GPU = synth.PAPERS_EDGES_PER_GPU
 
 
 def synthetic_partition(rank, world, device, seed=0, rows=PAPERS_ROWS_PER_GPU, edges=PAPERS_EDGES_PER_GPU,
-                        beta=0.05, hidden=128, group=None, mode=None):
-    """Generate this rank's shard directly on its GPU: power-law degrees inside the shard, a column is
-    uniform over the WHOLE graph with probability beta (remote with prob. beta*(P-1)/P) and uniform
-    inside the own range otherwise (the locality-controlled generator of SURVEY 8d)."""
-    n_total = rows * world
-    lo = rank * rows
-    deg, g = synth.powerlaw_degrees(rows, edges, seed=seed * 1000 + rank, device=device)
-    row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=device)
-    torch.cumsum(deg, 0, out=row_ptr[1:])
-    del deg
-    col = torch.empty(edges, dtype=torch.int64, device=device)
-    chunk = 1 << 26
-    for s in range(0, edges, chunk):
-        m = min(chunk, edges - s)
-        local = lo + torch.randint(0, rows, (m,), generator=g, device=device)
-        anywhere = torch.randint(0, n_total, (m,), generator=g, device=device)
-        remote = torch.rand(m, generator=g, device=device) < beta
-        col[s:s + m] = torch.where(remote, anywhere, local)
-        del local, anywhere, remote
+                        beta=0.05, hidden=128, group=None, mode=None, scaling="weak"):
+    """Generate this rank's shard directly on its GPU (synth.shard_csr: the locality-controlled
+    generator of SURVEY 8d) and wrap it in a PartitionedSpMM with X resident in the feature shard."""
+    row_ptr, col = synth.shard_csr(rank, world, rows, edges, beta, seed=seed, device=device)
     bounds = [k * rows for k in range(world + 1)]
     part = LocalPartition(rank, world, bounds, row_ptr, col, None)
     del col
-    desc = (f"unweighted spmm hidden={hidden} (fp32), papers100M-shaped power-law CSR partitioned by node range: "
-            f"{rows} rows + {edges} edges per GPU x {world} GPUs (= {n_total} nodes, {edges * world} edges), "
-            f"columns remote-eligible with prob beta={beta}, seed {seed} [BASELINE configs[4] shape, 1/8 of papers100M per GPU]")
+    desc = synth.shard_description(rows, edges, world, beta, seed, hidden, scaling)
     ps = PartitionedSpMM(part, device, group, global_nnz=edges * world, description=desc, mode=mode)
     gen = torch.Generator(device=device).manual_seed(seed + rank)
     if ps.mode == "p2p":

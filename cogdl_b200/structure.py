@@ -196,11 +196,30 @@ class CSRStructure:
 # ---------------------------------------------------------------------------------------------
 # Structure cache for the operator-level API, where the caller hands us bare (rowptr, colind)
 # tensors (reference signature csrspmm(rowptr, colind, x, csr_data, sym), operators/spmm.py:24).
-# Keyed on storage identity; the key tensors are kept alive by the entry so an address cannot be
-# recycled under a live key, and the in-place version counter catches mutation.
+#
+# Fast path: keyed on storage identity; the key tensors are kept alive by the entry so an address
+# cannot be recycled under a live key, and the in-place version counter catches mutation.
+#
+# Slow path: the reference's own dispatch passes `graph.row_indptr.int(), graph.col_indices.int()`
+# -- FRESH tensors on every call (cogdl/utils/spmm_utils.py:106) -- so identity never matches for a
+# module that captured the reference `spmm` before install().  Those calls are matched by CONTENT
+# against the most recent entries of the same shape (two device compares + one sync, ~tens of us)
+# instead of rebuilding the int32 copy, the hub plan (three kernels + a host sync + an argsort) and
+# possibly the transpose, and no entry is created for the short-lived tensors (no dead CSR copies
+# pinned by the cache).  The cache is bounded by entries AND by bytes.
 # ---------------------------------------------------------------------------------------------
 _CACHE = OrderedDict()
-_CACHE_CAP = 32
+_CACHE_CAP = 8
+_CACHE_MAX_BYTES = int(os.environ.get("COGDL_B200_STRUCT_CACHE_BYTES", str(8 << 30)))
+_CONTENT_SCAN = 4
+cache_stats = {"hit": 0, "content_hit": 0, "miss": 0}
+
+
+def _entry_bytes(st, rp, ci):
+    b = rp.numel() * rp.element_size() + ci.numel() * ci.element_size()
+    if st.rowptr.data_ptr() != rp.data_ptr():
+        b += st.rowptr.numel() * 4 + st.colind.numel() * 4
+    return b + 4 * st.nnz  # + edge_row of the plan, roughly
 
 
 def structure_for(rowptr, colind, n_cols=None):
@@ -211,11 +230,35 @@ def structure_for(rowptr, colind, n_cols=None):
         st, rp, ci, ver = ent
         if ver == (rp._version, ci._version):
             _CACHE.move_to_end(key)
+            cache_stats["hit"] += 1
             return st
+        del _CACHE[key]
+    # content match against recent entries of the same shape (the `.int()`-per-call caller)
+    scanned = 0
+    for k in reversed(_CACHE):
+        if scanned >= _CONTENT_SCAN:
+            break
+        if k[2:5] != key[2:5] or k[6] != n_cols:
+            continue
+        scanned += 1
+        st, rp, ci, ver = _CACHE[k]
+        if ver != (rp._version, ci._version):
+            continue
+        a_rp = rp if rp.dtype == rowptr.dtype else (st.rowptr if rowptr.dtype == torch.int32 else None)
+        a_ci = ci if ci.dtype == colind.dtype else (st.colind if colind.dtype == torch.int32 else None)
+        if a_rp is None or a_ci is None:
+            continue
+        if torch.equal(a_rp, rowptr) and torch.equal(a_ci, colind):
+            _CACHE.move_to_end(k)
+            cache_stats["content_hit"] += 1
+            return st
+    cache_stats["miss"] += 1
     st = CSRStructure.from_int64(rowptr, colind, n_cols)
     _CACHE[key] = (st, rowptr, colind, (rowptr._version, colind._version))
-    if len(_CACHE) > _CACHE_CAP:
-        _CACHE.popitem(last=False)
+    total = sum(_entry_bytes(*e[:3]) for e in _CACHE.values())
+    while len(_CACHE) > 1 and (len(_CACHE) > _CACHE_CAP or total > _CACHE_MAX_BYTES):
+        _, old = _CACHE.popitem(last=False)
+        total -= _entry_bytes(*old[:3])
     return st
 
 

@@ -85,3 +85,69 @@ def sym_norm_weights(row_ptr, col):
 def graph_stats(row_ptr):
     deg = row_ptr[1:] - row_ptr[:-1]
     return {"n": int(deg.numel()), "nnz": int(row_ptr[-1]), "max_deg": int(deg.max()), "mean_deg": float(deg.float().mean())}
+
+
+# ---------------------------------------------------------------------------------------------
+# Workload definitions shared by bench.py's two arms (ours / --impl reference).  This module is
+# deliberately free of any `cogdl_b200` import so the reference arm can load it by file path
+# without dlopen-ing libcogdl_b200.so.
+# ---------------------------------------------------------------------------------------------
+PAPERS_ROWS_PER_GPU = SHAPES["papers100M"][0] // 8      # 13 882 494
+PAPERS_EDGES_PER_GPU = SHAPES["papers100M"][1] // 8     # 201 960 734
+
+
+def arxiv_description(max_degree):
+    return ("spmm hidden=128 (fp32) on ogbn-arxiv-shaped power-law CSR: 169343 nodes, 1166243 edges + 169343 self "
+            "loops = 1335586 nnz, sym-normalised weights, max degree %d, seed 0 [BASELINE configs[1], GCN layer-1 "
+            "aggregation]" % int(max_degree))
+
+
+def shard_description(rows, edges, world, beta, seed, hidden=128, scaling="weak"):
+    n_total = rows * world
+    what = ("1/8 of papers100M per GPU" if scaling == "weak" else f"papers100M split {world}-way")
+    return (f"unweighted spmm hidden={hidden} (fp32), papers100M-shaped power-law CSR partitioned by node range: "
+            f"{rows} rows + {edges} edges per GPU x {world} GPUs (= {n_total} nodes, {edges * world} edges), "
+            f"columns remote-eligible with prob beta={beta}, seed {seed} [BASELINE configs[4] shape, {what}]")
+
+
+def shard_sizes(world, scaling="weak"):
+    """(rows, edges) per GPU: weak = 1/8 of papers100M per GPU whatever the GPU count;
+    strong = the whole papers100M-shaped graph split `world` ways."""
+    if scaling == "strong":
+        n, e = SHAPES["papers100M"]
+        return n // world, e // world
+    return PAPERS_ROWS_PER_GPU, PAPERS_EDGES_PER_GPU
+
+
+def shard_csr(rank, world, rows, edges, beta, seed=0, device="cpu", max_slice_edges=None):
+    """Rank `rank`'s shard of the locality-controlled papers100M-shaped graph: power-law
+    degrees inside the shard; a column is uniform over the WHOLE graph with probability beta (remote
+    with prob. beta*(P-1)/P) and uniform inside the own node range otherwise.  Returns
+    (row_ptr int64 [r+1], col int64 GLOBAL ids [nnz]).  max_slice_edges: keep only the leading rows
+    holding at least that many edges (CPU baseline sample; the degree law is still the full shard's)."""
+    n_total = rows * world
+    lo = rank * rows
+    deg, g = powerlaw_degrees(rows, edges, seed=seed * 1000 + rank, device=device)
+    row_ptr = torch.zeros(rows + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=row_ptr[1:])
+    del deg
+    n_edges = edges
+    if max_slice_edges is not None and max_slice_edges < edges:
+        r = int(torch.searchsorted(row_ptr, torch.tensor([max_slice_edges], device=device, dtype=torch.int64))[0])
+        r = max(1, min(r, rows))
+        row_ptr = row_ptr[: r + 1].clone()
+        n_edges = int(row_ptr[-1])
+    col = torch.empty(n_edges, dtype=torch.int64, device=device)
+    chunk = 1 << 26
+    for s in range(0, n_edges, chunk):
+        m = min(chunk, n_edges - s)
+        local = lo + torch.randint(0, rows, (m,), generator=g, device=device)
+        if beta > 0:
+            anywhere = torch.randint(0, n_total, (m,), generator=g, device=device)
+            remote = torch.rand(m, generator=g, device=device) < beta
+            col[s:s + m] = torch.where(remote, anywhere, local)
+            del anywhere, remote
+        else:
+            col[s:s + m] = local
+        del local
+    return row_ptr, col

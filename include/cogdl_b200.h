@@ -54,6 +54,10 @@ COGDL_B200_API const char *cogdl_b200_last_error(void);
 COGDL_B200_API int cogdl_b200_check_device(void);
 /* Number of kernels this library has launched in this process (all threads). */
 COGDL_B200_API int64_t cogdl_b200_launch_count(void);
+/* Thread-local description of the kernel instantiation chosen by the last dispatching call on this
+ * thread (e.g. "stream_kernel<float4,NV=1,weighted,SRC_ONE,U=4>"); "" before the first call.  Lets a
+ * harness check that a profile it cites is of the kernel that actually ran. */
+COGDL_B200_API const char *cogdl_b200_last_kernel(void);
 
 /* ---------------------------------------------------------------------------------------
  * Hub plan: how rows with more than `chunk_edges` edges are cut into fixed-size edge chunks

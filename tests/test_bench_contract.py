@@ -31,3 +31,53 @@ def test_reference_arm_other_ranks_exit_silently():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_multi_gpu_times_the_shard_workload_and_never_loads_the_product_library():
+    """N > 1: rank 0 times a row slice of its papers100M-shaped shard (same workload string as our arm
+    builds from synth.shard_description), and the process must not have dlopen-ed libcogdl_b200.so."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", COGDL_B200_BENCH_SHARD_DIV="100")
+    code = (
+        "import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '3'];"
+        "runpy.run_path('bench.py', run_name='__main__');"
+        "maps = open('/proc/self/maps').read();"
+        "assert 'libcogdl_b200' not in maps, 'reference arm loaded the product library';"
+        "assert 'cogdl_b200' not in sys.modules"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "weak"
+    assert "papers100M-shaped" in d["config"]["workload"] and "beta=0.05" in d["config"]["workload"]
+    assert d["cpu_baseline"]["cores"] >= 1 and "threads_sweep_edges_per_s" in d["cpu_baseline"]
+
+
+def test_both_arms_build_the_same_workload_strings():
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    bench = importlib.import_module("bench")
+    synth = bench.load_synth()
+    from cogdl_b200 import synth as pkg_synth
+
+    assert synth.arxiv_description(123) == pkg_synth.arxiv_description(123)
+    a = synth.shard_description(10, 20, 4, 0.25, 0, 128, "strong")
+    assert a == pkg_synth.shard_description(10, 20, 4, 0.25, 0, 128, "strong") and "split 4-way" in a
+    assert synth.shard_sizes(2, "strong") == (111059956 // 2, 1615685872 // 2)
+    assert synth.shard_sizes(2, "weak") == synth.shard_sizes(8, "weak") == (111059956 // 8, 1615685872 // 8)
+
+
+def test_cpu_thread_sweep_takes_the_fastest_median():
+    sys.path.insert(0, ROOT)
+    import importlib
+    import time
+
+    bench = importlib.import_module("bench")
+    state = {"t": 1}
+    cost = {8: 0.004, 4: 0.001, 2: 0.006, 16: 0.02, 32: 0.02, 1: 0.01}
+
+    def call():
+        time.sleep(cost.get(state["t"], 0.01))
+
+    best, res = bench.cpu_thread_sweep(call, lambda t: state.update(t=t), 8, reps=3)
+    assert best == 4 and set(res) == {8, 4, 2} and state["t"] == 4

@@ -108,7 +108,8 @@ def test_spmm_two_source(dev):
     assert np.array_equal(y, ref)
 
 
-def test_spmm_peer_form_single_gpu(dev):
+@pytest.mark.parametrize("F", [128, 16, 40, 64, 8, 256])
+def test_spmm_peer_form_single_gpu(dev, F):
     """The fused-gather kernel (cogdl_b200_spmm_csr_f32_peers) with the 'peers' being three separate
     buffers on this GPU: checks the (owner << shift | row) column decoding and the per-owner base
     pointers without needing NVLink (the multi-GPU run is tools/dist_gpu_check.py)."""
@@ -120,7 +121,6 @@ def test_spmm_peer_form_single_gpu(dev):
     rp, ci, n_cols = case("two_hubs")
     n = rp.shape[0] - 1
     rng = np.random.default_rng(14)
-    F = 128
     X = rng.standard_normal((n_cols, F)).astype(np.float32)
     val = rng.random(ci.shape[0]).astype(np.float32)
     ref = oracle.spmm_csr(rp, ci, val, X)
