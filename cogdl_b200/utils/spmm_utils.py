@@ -55,16 +55,15 @@ def check_fused_gat():
 def _structure(graph):
     if hasattr(graph, "structure"):
         return graph.structure()
-    # a real cogdl.data.Graph: cache our structure on its adjacency object
-    adj = graph._adj
-    st = adj.__dict__.get("_b200_structure")
-    key = (graph.row_indptr.data_ptr(), graph.col_indices.data_ptr())
-    if st is None or st[0] != key:
-        from ..structure import CSRStructure
+    # A real cogdl.data.Graph.  Its Adjacency filters attribute names through __getitem__/keys
+    # (cogdl/data/data.py:352-375: a single leading underscore is stripped, only `keys` survive
+    # copy.copy in local_graph()), so nothing can be parked on the object itself; the int32 CSR, hub
+    # plan and transpose live in the storage-keyed structure cache instead.  graph.row_indptr /
+    # col_indices return the SAME tensors on every call and local_graph()'s shallow copies share their
+    # storage (data.py:381-386), so this is a dictionary hit per call, never a rebuild.
+    from ..structure import structure_for
 
-        st = (key, CSRStructure.from_int64(graph.row_indptr, graph.col_indices, n_cols=graph.num_nodes))
-        adj.__dict__["_b200_structure"] = st
-    return st[1]
+    return structure_for(graph.row_indptr, graph.col_indices, graph.num_nodes)
 
 
 def spmm(graph, x, actnn=False, fast_spmm=None, fast_spmm_cpu=None):
