@@ -17,5 +17,6 @@ from .utils.spmm_utils import (  # noqa: E402,F401
 )
 from .operators import csrspmm, csr_edge_softmax, csrmhspmm, scatter_max, fused_gat_func  # noqa: E402,F401
 from .install import install  # noqa: E402,F401
+from . import sampling  # noqa: E402,F401
 
 __version__ = "0.1.0"

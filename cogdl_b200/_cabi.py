@@ -71,6 +71,13 @@ SIGNATURES = {
     "cogdl_b200_coo2csr_workspace_bytes": (_i64, [_i64, _i64]),
     "cogdl_b200_coo2csr_index": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "cogdl_b200_narrow_i64_i32": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    "cogdl_b200_sample_draw": (ctypes.c_uint64, [ctypes.c_uint64, _i64, _i64]),
+    "cogdl_b200_sample_workspace_bytes": (_i64, [_i64, _i64]),
+    "cogdl_b200_sample_adj_count": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "cogdl_b200_sample_adj_fill": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, ctypes.c_uint64, _vp, _i64, _vp,
+                                                  _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cogdl_b200_subgraph_count": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "cogdl_b200_subgraph_fill": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -53,6 +53,39 @@ def install(rebind_dispatch=True):
             setattr(mod, k, v)
 
     patched = []
+    # Device sampler: Graph.sample_adj / csr_subgraph (cogdl/data/data.py:792-874) resolve the
+    # module globals `sample_adj_c` / `subgraph_c`.  CUDA graphs go to the device sampler; CPU graphs keep
+    # the reference's own host functions (they are not ours to replace: no CPU path in this package).
+    import cogdl.data.data as ref_data
+    from . import sampling
+
+    ref_sample, ref_subgraph = getattr(ref_data, "sample_adj_c", None), getattr(ref_data, "subgraph_c", None)
+    if not getattr(ref_sample, "_cogdl_b200", False):
+        def sample_adj_c(indptr, indices, node_idx, num_neighbors=-1, replace=True):
+            if not indptr.is_cuda:
+                if ref_sample is None:
+                    raise RuntimeError("cogdl.operators.sample failed to load and the graph is on the CPU")
+                return ref_sample(indptr, indices, node_idx, num_neighbors, replace)
+            import torch
+
+            node_idx = torch.as_tensor(node_idx, dtype=torch.int64).to(indptr.device)
+            rp, ci, nodes, edges = sampling.sample_adj(indptr, indices, node_idx, num_neighbors, replace)
+            # data.py:818-820 pads row_ptr for the new (edge-less) nodes with a CPU tensor; hand it over padded
+            pad = nodes.numel() + 1 - rp.numel()
+            if pad > 0:
+                rp = torch.cat([rp, rp[-1:].expand(pad)])
+            return rp, ci, nodes, edges
+
+        def subgraph_c(indptr, indices, node_idx):
+            if not indptr.is_cuda:
+                if ref_subgraph is None:
+                    raise RuntimeError("cogdl.operators.sample failed to load and the graph is on the CPU")
+                return ref_subgraph(indptr, indices, node_idx)
+            return sampling.subgraph(indptr, indices, node_idx.to(indptr.device))
+
+        sample_adj_c._cogdl_b200 = subgraph_c._cogdl_b200 = True
+        ref_data.sample_adj_c, ref_data.subgraph_c = sample_adj_c, subgraph_c
+        patched += ["cogdl.data.data.sample_adj_c", "cogdl.data.data.subgraph_c"]
     if rebind_dispatch:
         names = ["spmm", "edge_softmax", "mh_spmm", "fused_gat_op", "check_fused_gat", "SpMM", "EdgeSoftmax",
                  "MultiHeadSpMM", "FusedGATOp"]

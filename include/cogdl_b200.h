@@ -270,6 +270,52 @@ COGDL_B200_API int cogdl_b200_coo2csr_index(const int64_t *row, int64_t nnz, int
  * must fit).  Replaces the per-call `.int()` casts of cogdl/utils/spmm_utils.py:106. */
 COGDL_B200_API int cogdl_b200_narrow_i64_i32(const int64_t *in, int32_t *out, int64_t n, cogdl_b200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Neighbour sampling and induced subgraphs on the device.  int64 CSR in / int64 out, as
+ * cogdl.data.Graph stores it (row_ptr, col).
+ * Replaces  sampler.sample_adj(indptr, indices, node_idx, num_neighbors, replace)
+ *             -> (out_indptr, out_indices, out_nodes, out_edges)   cogdl/operators/sample/sample.cpp:6-146
+ *           sampler.subgraph(indptr, indices, node_idx)
+ *             -> (out_indptr, out_indices, arange, out_edges)      cogdl/operators/sample/sample.cpp:148-188
+ * (single-thread host loops called per mini-batch by Graph.sample_adj / csr_subgraph, data.py:792-874).
+ *
+ * Results are IDENTICAL to the reference's sequential loops for any emitted edge list: out_nodes =
+ * batch nodes, then new source nodes in order of first appearance; out_indices = their positions.
+ * Which edges are emitted: num_neighbors < 0 -> every edge of each batch row (CSR order);
+ * replace != 0 -> num_neighbors draws with replacement per row (none for a degree-0 row; the
+ * reference divides by zero there); else min(deg, num_neighbors) DISTINCT edges by Floyd's algorithm
+ * in insertion order (the reference's variant draws `rand() % j` and is biased -- fixed, see
+ * sampler.cu).  Every draw is cogdl_b200_sample_draw(seed, batch slot, draw index): a counter-based
+ * generator, so batches are reproducible and bit-checkable (the reference uses unseeded libc rand()).
+ *
+ * Two phases because the output sizes are data dependent and the caller owns every buffer:
+ *   1. ..._count : out_indptr[n_batch+1] (device).  Read out_indptr[n_batch] = n_edges on the host.
+ *   2. ..._fill  : out_indices / out_edges [n_edges], out_nodes [capacity n_batch + n_edges],
+ *                  *n_out_nodes_dev (device int64) = number of out_nodes entries written.
+ * `assoc`: device int32[num_nodes] scratch, every entry COGDL_B200_SAMPLE_UNSEEN on entry; restored
+ * before the fill returns (subgraph: marked by _count, restored by _fill -- always call both).
+ * node_idx entries must be distinct.  n_batch + n_edges must fit int32.
+ * `workspace`: >= cogdl_b200_sample_workspace_bytes(n_batch, n_edges) bytes (n_edges = 0 for _count).
+ * ------------------------------------------------------------------------------------- */
+#define COGDL_B200_SAMPLE_UNSEEN 0x7fffffff
+COGDL_B200_API uint64_t cogdl_b200_sample_draw(uint64_t seed, int64_t slot, int64_t k);
+COGDL_B200_API int64_t cogdl_b200_sample_workspace_bytes(int64_t n_batch, int64_t n_edges);
+COGDL_B200_API int cogdl_b200_sample_adj_count(const int64_t *indptr, const int64_t *node_idx, int64_t n_batch,
+                                int64_t num_neighbors, int32_t replace, int64_t *out_indptr, void *workspace,
+                                int64_t workspace_bytes, cogdl_b200_stream_t stream);
+COGDL_B200_API int cogdl_b200_sample_adj_fill(const int64_t *indptr, const int64_t *indices, const int64_t *node_idx,
+                               int64_t n_batch, int64_t num_nodes, int64_t num_neighbors, int32_t replace,
+                               uint64_t seed, const int64_t *out_indptr, int64_t n_edges, int32_t *assoc,
+                               int64_t *out_indices, int64_t *out_edges, int64_t *out_nodes,
+                               int64_t *n_out_nodes_dev, void *workspace, int64_t workspace_bytes,
+                               cogdl_b200_stream_t stream);
+COGDL_B200_API int cogdl_b200_subgraph_count(const int64_t *indptr, const int64_t *indices, const int64_t *node_idx,
+                              int64_t n_sub, int32_t *assoc, int64_t *out_indptr, void *workspace,
+                              int64_t workspace_bytes, cogdl_b200_stream_t stream);
+COGDL_B200_API int cogdl_b200_subgraph_fill(const int64_t *indptr, const int64_t *indices, const int64_t *node_idx,
+                             int64_t n_sub, int32_t *assoc, const int64_t *out_indptr, int64_t *out_indices,
+                             int64_t *out_edges, cogdl_b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -210,3 +210,48 @@ def ref_module(name, variant="asis"):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+# ----------------------------------------------------------------------------- sampler
+_u64 = ctypes.c_uint64
+
+
+def sample_draw(seed, slot, k):
+    f = lib().oracle_sample_draw
+    f.restype = _u64
+    return int(f(_u64(seed), _i64(slot), _i64(k)))
+
+
+def sample_adj(indptr, indices, node_idx, num_neighbors=-1, replace=True, seed=0, floyd_variant=0):
+    """(out_indptr, out_indices, out_nodes, out_edges) -- cogdl/operators/sample/sample.cpp:6-146 with the
+    counter-based generator shared with the CUDA path (see oracle.c)."""
+    indptr, indices, node_idx = _a(indptr, np.int64), _a(indices, np.int64), _a(node_idx, np.int64)
+    n, nb = indptr.shape[0] - 1, node_idx.shape[0]
+    deg = indptr[node_idx + 1] - indptr[node_idx]
+    cap = int(deg.sum()) if num_neighbors < 0 else int(nb * num_neighbors)
+    out_indptr = np.zeros(nb + 1, np.int64)
+    out_indices = np.empty(max(cap, 1), np.int64)
+    out_edges = np.empty(max(cap, 1), np.int64)
+    out_nodes = np.empty(nb + max(cap, 1), np.int64)
+    f = lib().oracle_sample_adj
+    f.restype = _i64
+    n_nodes = f(_p(indptr, _i64p), _p(indices, _i64p), _p(node_idx, _i64p), _i64(nb), _i64(n), _i64(num_neighbors),
+                ctypes.c_int(int(replace)), _u64(seed), ctypes.c_int(floyd_variant), _p(out_indptr, _i64p),
+                _p(out_indices, _i64p), _p(out_edges, _i64p), _p(out_nodes, _i64p), _i64(cap))
+    assert n_nodes >= 0
+    ne = int(out_indptr[-1])
+    return out_indptr, out_indices[:ne].copy(), out_nodes[:n_nodes].copy(), out_edges[:ne].copy()
+
+
+def subgraph(indptr, indices, node_idx):
+    """(out_indptr, out_indices, out_edges) -- cogdl/operators/sample/sample.cpp:148-188."""
+    indptr, indices, node_idx = _a(indptr, np.int64), _a(indices, np.int64), _a(node_idx, np.int64)
+    n, ns = indptr.shape[0] - 1, node_idx.shape[0]
+    cap = max(int((indptr[node_idx + 1] - indptr[node_idx]).sum()), 1)
+    out_indptr = np.zeros(ns + 1, np.int64)
+    out_indices, out_edges = np.empty(cap, np.int64), np.empty(cap, np.int64)
+    f = lib().oracle_subgraph
+    f.restype = _i64
+    ne = f(_p(indptr, _i64p), _p(indices, _i64p), _p(node_idx, _i64p), _i64(ns), _i64(n), _p(out_indptr, _i64p),
+           _p(out_indices, _i64p), _p(out_edges, _i64p))
+    return out_indptr, out_indices[:ne].copy(), out_edges[:ne].copy()

@@ -340,3 +340,109 @@ ORACLE_API void oracle_gat_fwd_f32(const int32_t *rowptr, const int32_t *colind,
     free(acc);
   }
 }
+
+/* ------------------------------------------------------------------------
+ * Neighbour sampling and induced subgraphs.
+ * Restates cogdl/operators/sample/sample.cpp:6-146 (sample_adj) and :148-188
+ * (subgraph_cpu) as the sequential host loops they are:
+ *   - out_nodes = batch nodes, then every new source node in order of first
+ *     appearance (the running `num_nodes` counter, sample.cpp:44-47 etc.);
+ *   - out_indices[q] = id of edge q's source in out_nodes; out_edges[q] = the
+ *     global CSR position of the edge; out_indptr = running edge count.
+ * Randomness: the reference uses libc rand() (unseeded, not reproducible).  The
+ * oracle and the CUDA path share a COUNTER-BASED generator instead: draw k of
+ * batch slot i = mix64(mix64(seed + i*0xD1342543DE82EF95) + k), mix64 = the
+ * splitmix64 finaliser.  `floyd_variant` selects the without-replacement rule:
+ *   0: Robert Floyd's algorithm, t ~ U{0..j}   (what the CUDA path implements)
+ *   1: the reference's loop literally, t = draw % j  (sample.cpp:101-104), kept so
+ *      tests can show its bias (degree 2, k = 1 always yields the first edge).
+ * Edges of a row are emitted in insertion order (the reference iterates a
+ * std::unordered_set: unspecified order).  replace on a degree-0 row emits
+ * nothing (the reference would divide by zero).
+ * Returns the number of out_nodes; out_nodes needs room for n_batch + n_edges.
+ * ---------------------------------------------------------------------- */
+static uint64_t oracle_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+ORACLE_API uint64_t oracle_sample_draw(uint64_t seed, int64_t slot, int64_t k) {
+  return oracle_mix64(oracle_mix64(seed + (uint64_t)slot * 0xD1342543DE82EF95ull) + (uint64_t)k);
+}
+
+ORACLE_API int64_t oracle_sample_adj(const int64_t *indptr, const int64_t *indices, const int64_t *node_idx,
+                                     int64_t n_batch, int64_t num_nodes, int64_t k, int replace, uint64_t seed,
+                                     int floyd_variant, int64_t *out_indptr, int64_t *out_indices,
+                                     int64_t *out_edges, int64_t *out_nodes, int64_t edge_capacity) {
+  int64_t *assoc = (int64_t *)malloc((size_t)(num_nodes > 0 ? num_nodes : 1) * sizeof(int64_t));
+  for (int64_t v = 0; v < num_nodes; ++v) assoc[v] = -1;
+  for (int64_t i = 0; i < n_batch; ++i) {
+    assoc[node_idx[i]] = i;
+    out_nodes[i] = node_idx[i];
+  }
+  int64_t n_nodes = n_batch, n_edges = 0;
+  out_indptr[0] = 0;
+  for (int64_t i = 0; i < n_batch; ++i) {
+    const int64_t node = node_idx[i];
+    const int64_t rs = indptr[node], deg = indptr[node + 1] - rs;
+    int64_t cnt;
+    if (k < 0) cnt = deg;
+    else if (replace) cnt = deg > 0 ? k : 0;
+    else cnt = deg < k ? deg : k;
+    if (n_edges + cnt > edge_capacity) { free(assoc); return -1; }
+    int64_t *picks = out_edges + n_edges;
+    if (k < 0 || (!replace && deg <= k)) {
+      for (int64_t t = 0; t < cnt; ++t) picks[t] = rs + t;
+    } else if (replace) {
+      for (int64_t t = 0; t < cnt; ++t) picks[t] = rs + (int64_t)(oracle_sample_draw(seed, i, t) % (uint64_t)deg);
+    } else {
+      int64_t have = 0;
+      for (int64_t j = deg - k; j < deg; ++j, ++have) {
+        const uint64_t r = oracle_sample_draw(seed, i, have);
+        const int64_t t = floyd_variant ? (j > 0 ? (int64_t)(r % (uint64_t)j) : 0) : (int64_t)(r % (uint64_t)(j + 1));
+        int taken = 0;
+        for (int64_t q = 0; q < have; ++q) taken |= (picks[q] == rs + t);
+        picks[have] = rs + (taken ? j : t);
+      }
+    }
+    for (int64_t t = 0; t < cnt; ++t) {
+      const int64_t src = indices[picks[t]];
+      if (assoc[src] == -1) {
+        assoc[src] = n_nodes;
+        out_nodes[n_nodes++] = src;
+      }
+      out_indices[n_edges + t] = assoc[src];
+    }
+    n_edges += cnt;
+    out_indptr[i + 1] = n_edges;
+  }
+  free(assoc);
+  return n_nodes;
+}
+
+/* Restates sample.cpp:148-188 (subgraph_cpu): edges between listed nodes, relabelled to list positions,
+ * CSR order kept.  Returns the number of edges; outputs need room for the rows' total degree. */
+ORACLE_API int64_t oracle_subgraph(const int64_t *indptr, const int64_t *indices, const int64_t *node_idx,
+                                   int64_t n_sub, int64_t num_nodes, int64_t *out_indptr, int64_t *out_indices,
+                                   int64_t *out_edges) {
+  int64_t *assoc = (int64_t *)malloc((size_t)(num_nodes > 0 ? num_nodes : 1) * sizeof(int64_t));
+  for (int64_t v = 0; v < num_nodes; ++v) assoc[v] = -1;
+  for (int64_t i = 0; i < n_sub; ++i) assoc[node_idx[i]] = i;
+  int64_t n_edges = 0;
+  out_indptr[0] = 0;
+  for (int64_t i = 0; i < n_sub; ++i) {
+    const int64_t node = node_idx[i];
+    for (int64_t e = indptr[node]; e < indptr[node + 1]; ++e) {
+      const int64_t a = assoc[indices[e]];
+      if (a > -1) {
+        out_indices[n_edges] = a;
+        out_edges[n_edges] = e;
+        ++n_edges;
+      }
+    }
+    out_indptr[i + 1] = n_edges;
+  }
+  free(assoc);
+  return n_edges;
+}

@@ -261,3 +261,46 @@ def test_install_registers_backend_in_reference_package():
     import cogdl.operators.scatter_max as ref_sm
 
     assert ref_sm.scatter_max is cogdl_b200.scatter_max
+
+
+def test_oracle_sampler_is_pinned_to_the_reference_sample_cpp():
+    """No-randomness paths of sample.cpp (sample_adj with num_neighbors = -1, subgraph) compiled from the
+    reference's own source (oracle/_ref) vs the oracle restatement: every output array identical."""
+    if not oracle.ref_available("sampler", "asis"):
+        pytest.skip("oracle/_ref not built")
+    smp = oracle.ref_module("sampler", "asis")
+    rng = np.random.default_rng(0)
+    for n, hi in ((500, 12), (3000, 40), (40, 3)):
+        deg = rng.integers(0, hi, n)
+        indptr = np.zeros(n + 1, np.int64)
+        indptr[1:] = np.cumsum(deg)
+        indices = rng.integers(0, n, int(indptr[-1])).astype(np.int64)
+        batch = rng.permutation(n)[: max(1, n // 6)].astype(np.int64)
+        t = [torch.from_numpy(a) for a in (indptr, indices, batch)]
+        ref = smp.sample_adj(t[0], t[1], t[2], -1, False)
+        got = oracle.sample_adj(indptr, indices, batch, -1, False)
+        assert all(np.array_equal(a.numpy(), b) for a, b in zip(ref, got))
+        ref = smp.subgraph(t[0], t[1], t[2])
+        got = oracle.subgraph(indptr, indices, batch)
+        assert np.array_equal(ref[0].numpy(), got[0]) and np.array_equal(ref[1].numpy(), got[1])
+        assert np.array_equal(ref[3].numpy(), got[2]) and np.array_equal(ref[2].numpy(), np.arange(batch.shape[0]))
+        # random paths: the row sizes and the first-appearance numbering obey the reference's rules
+        for size, replace in ((4, True), (4, False)):
+            oi, oc, on, oe = oracle.sample_adj(indptr, indices, batch, size, replace, seed=7)
+            d = indptr[batch + 1] - indptr[batch]
+            want = np.where(d > 0, size, 0) if replace else np.minimum(d, size)
+            assert np.array_equal(np.diff(oi), want)
+            assert np.array_equal(on[: batch.shape[0]], batch) and np.array_equal(on[oc], indices[oe])
+            first = {}
+            for q, s_ in enumerate(indices[oe]):
+                first.setdefault(int(s_), q)
+            new = [s_ for s_ in sorted(first, key=first.get) if s_ not in set(batch.tolist())]
+            assert on[batch.shape[0]:].tolist() == new
+
+
+def test_sampler_generator_matches_between_library_and_oracle():
+    import cogdl_b200
+
+    lib = cogdl_b200._cabi.load()
+    for seed, slot, k in ((0, 0, 0), (1, 2, 3), (2**63 + 5, 10**9, 77), (2**64 - 1, 2**40, 2**33)):
+        assert int(lib.cogdl_b200_sample_draw(seed, slot, k)) == oracle.sample_draw(seed, slot, k)

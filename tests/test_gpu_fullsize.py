@@ -194,11 +194,17 @@ def test_c4_spmm_f128_products_slice_and_hubs(dev, products):
     unsplit = deg <= st.chunk_edges
     assert unsplit.sum() > 100000 and (~unsplit).sum() >= 64
     assert np.array_equal(got[unsplit], ref[unsplit]), "unsplit rows: bit-identical to the reference CPU order"
-    assert rowwise_err(got, ref) <= TOL
-    # hub rows against an fp64 sum as well
-    hub_ids = np.nonzero(~unsplit)[0][:256]
-    ref64 = np.stack([xh[sci[srp[j]:srp[j + 1]]].astype(np.float64).sum(0) for j in hub_ids])
-    assert rowwise_err(got[hub_ids], ref64) <= TOL
+    # rows up to 4096 edges: the fp32 sequential oracle is still a valid yardstick (its own error ~ eps*sqrt(deg)/5)
+    mid = deg <= 4096
+    assert rowwise_err(got[mid], ref[mid]) <= TOL
+    # heavier hubs (up to ~6e5 edges here): the sequential fp32 sum is itself > 1e-5 off -> fp64 yardstick
+    big = np.nonzero(~mid)[0]
+    assert big.size >= 32
+    ref64 = np.stack([xh[sci[srp[j]:srp[j + 1]]].astype(np.float64).sum(0) for j in big])
+    assert rowwise_err(got[big], ref64) <= TOL
+    some = np.nonzero(~unsplit & mid)[0][:512]
+    ref64s = np.stack([xh[sci[srp[j]:srp[j + 1]]].astype(np.float64).sum(0) for j in some])
+    assert rowwise_err(got[some], ref64s) <= TOL
 
 
 # ------------------------------------------------------------------------------------------- C5
