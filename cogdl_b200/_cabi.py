@@ -61,6 +61,9 @@ SIGNATURES = {
     "cogdl_b200_csr2csc_workspace_bytes": (_i64, [_i64, _i64]),
     "cogdl_b200_csr2csc": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cogdl_b200_gather_rows_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "cogdl_b200_edge_softmax_scratch_bytes": (_i64, [_i64, _i64]),
+    "cogdl_b200_gat_attn_bwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _i64, _plan_p, _vp]),
+    "cogdl_b200_edge_colsum_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_edge_softmax_fwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_edge_softmax_bwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_mhspmm_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _plan_p, _vp]),
@@ -97,7 +100,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.cogdl_b200_abi_version() != 3:
+        if lib.cogdl_b200_abi_version() != 4:
             raise ImportError("libcogdl_b200.so ABI version mismatch")
         _lib = lib
     return _lib

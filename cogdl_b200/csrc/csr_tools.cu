@@ -74,6 +74,57 @@ __global__ void narrow_kernel(const int64_t *__restrict__ in, int *out, int64_t 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int)in[i];
 }
 
+// Column sums of an edge-aligned [nnz, H] tensor through the transpose (colptr, perm): one thread per
+// (item, head), sequential over the item's entries => deterministic.  Hub columns are cut into the
+// plan's chunks (pass 1: partial per chunk slot; pass 2: the thread of the row's FIRST slot adds the
+// partials in chunk order).  Adjacent threads are adjacent heads of one edge row: 4*H contiguous bytes.
+struct ColsumParams {
+  const int *colptr;
+  const int *perm;
+  const float *e;
+  float *out;
+  int64_t n_cols;
+  int H;
+  HubView hub;
+  float *part;
+};
+
+__global__ void colsum_chunk_kernel(const ColsumParams p) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = tid / p.H;
+  const int h = (int)(tid - item * p.H);
+  if (item >= p.hub.n_chunks) return;
+  const int2 c = __ldg(p.hub.chunks + item);
+  const int cb = __ldg(p.colptr + c.x) + ((int)item - c.y) * p.hub.chunk_edges;
+  const int ce = min(cb + p.hub.chunk_edges, __ldg(p.colptr + c.x + 1));
+  float acc = 0.f;
+  for (int q = cb; q < ce; ++q) acc += __ldg(p.e + (int64_t)__ldg(p.perm + q) * p.H + h);
+  p.part[item * p.H + h] = acc;
+}
+
+__global__ void colsum_kernel(const ColsumParams p) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = tid / p.H;
+  const int h = (int)(tid - item * p.H);
+  if (item < p.hub.n_chunks) {
+    const int2 c = __ldg(p.hub.chunks + item);
+    if (c.y != (int)item) return;             // only the first slot of a hub column writes
+    const int deg = __ldg(p.colptr + c.x + 1) - __ldg(p.colptr + c.x);
+    const int n = (deg + p.hub.chunk_edges - 1) / p.hub.chunk_edges;
+    float acc = 0.f;
+    for (int q = 0; q < n; ++q) acc += p.part[(item + q) * p.H + h];
+    p.out[(int64_t)c.x * p.H + h] = acc;
+    return;
+  }
+  const int64_t col = item - p.hub.n_chunks;
+  if (col >= p.n_cols) return;
+  const int cb = __ldg(p.colptr + col), ce = __ldg(p.colptr + col + 1);
+  if (p.hub.chunk_edges > 0 && ce - cb > p.hub.chunk_edges) return;   // hub column: handled above
+  float acc = 0.f;
+  for (int q = cb; q < ce; ++q) acc += __ldg(p.e + (int64_t)__ldg(p.perm + q) * p.H + h);
+  p.out[col * p.H + h] = acc;
+}
+
 static unsigned grid_for(int64_t n) {
   int64_t b = ceil_div(n, 256);
   if (b > 148 * 32) b = 148 * 32;
@@ -139,6 +190,33 @@ extern "C" int cogdl_b200_gather_rows_f32(const int32_t *perm, const float *in, 
   CB_REQUIRE(perm && in && out, "cogdl_b200_gather_rows_f32: null pointer");
   CB_REQUIRE(H < 0x7fffffffLL, "cogdl_b200_gather_rows_f32: H must fit int32");
   gather_rows_kernel<<<grid_for(nnz * H), 256, 0, (cudaStream_t)stream>>>(perm, in, out, nnz * H, (int)H);
+  CB_LAUNCH_CHECK();
+  return COGDL_B200_OK;
+}
+
+extern "C" int cogdl_b200_edge_colsum_f32(const int32_t *colptr, const int32_t *perm, const float *e, float *out,
+                                          int64_t n_cols, int64_t H, const cogdl_b200_hub_plan_t *plan,
+                                          cogdl_b200_stream_t stream) {
+  CB_REQUIRE(n_cols >= 0 && H >= 0, "cogdl_b200_edge_colsum_f32: negative size");
+  if (n_cols == 0 || H == 0) return COGDL_B200_OK;
+  CB_REQUIRE(colptr && perm && e && out, "cogdl_b200_edge_colsum_f32: null pointer");
+  CB_REQUIRE(H < 0x7fffffffLL && n_cols < 0x7fffffffLL, "cogdl_b200_edge_colsum_f32: sizes must fit int32");
+  ColsumParams p;
+  p.colptr = colptr; p.perm = perm; p.e = e; p.out = out; p.n_cols = n_cols; p.H = (int)H;
+  p.hub = hub_view(plan);
+  p.hub.n_segs = 0;
+  int rc = check_plan(plan, (int64_t)p.hub.n_chunks * H * (int64_t)sizeof(float));
+  if (rc) return rc;
+  p.part = reinterpret_cast<float *>(p.hub.partials);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p.hub.n_chunks > 0) {
+    const int64_t b = ceil_div((int64_t)p.hub.n_chunks * H, 256);
+    colsum_chunk_kernel<<<(unsigned)b, 256, 0, s>>>(p);
+    CB_LAUNCH_CHECK();
+  }
+  const int64_t blocks = ceil_div(((int64_t)p.hub.n_chunks + n_cols) * H, 256);
+  CB_REQUIRE(blocks <= 0x7fffffffLL, "cogdl_b200_edge_colsum_f32: problem too large for one launch");
+  colsum_kernel<<<(unsigned)blocks, 256, 0, s>>>(p);
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;
 }

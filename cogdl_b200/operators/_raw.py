@@ -83,6 +83,11 @@ def gather_rows_raw(perm, x):
     return out
 
 
+def _es_scratch(st, H):
+    """Bytes of plan scratch the split-row softmax needs (per hub chunk and head: (max, sum) + a partial)."""
+    return st.plan.n_chunks * H * 12 if st.chunk_edges > 0 else 0
+
+
 def edge_softmax_fwd_raw(st: CSRStructure, e):
     dev = require_cuda(e)
     e = _f32c(e, "edge values")
@@ -90,7 +95,7 @@ def edge_softmax_fwd_raw(st: CSRStructure, e):
         raise ValueError(f"edge values must be [nnz={st.nnz}, H], got {tuple(e.shape)}")
     with torch.cuda.device(dev):
         out = torch.empty_like(e)
-        plan, keep = st.plan_struct(0)
+        plan, keep = st.plan_struct(_es_scratch(st, e.shape[1]))
         _cabi.call("cogdl_b200_edge_softmax_fwd_f32", _ptr(st.rowptr), _ptr(e), _ptr(out), st.n_rows, e.shape[1],
                    plan, _stream(dev))
         del keep
@@ -102,7 +107,7 @@ def edge_softmax_bwd_raw(st: CSRStructure, y, g):
     y, g = _f32c(y, "y"), _f32c(g, "g")
     with torch.cuda.device(dev):
         out = torch.empty_like(y)
-        plan, keep = st.plan_struct(0)
+        plan, keep = st.plan_struct(_es_scratch(st, y.shape[1]))
         _cabi.call("cogdl_b200_edge_softmax_bwd_f32", _ptr(st.rowptr), _ptr(y), _ptr(g), _ptr(out), st.n_rows,
                    y.shape[1], plan, _stream(dev))
         del keep
@@ -171,8 +176,37 @@ def gat_fwd_raw(st: CSRStructure, h_l, h_r, feat, slope, want_att):
     with torch.cuda.device(dev):
         out = torch.empty((st.n_rows, H, F), dtype=torch.float32, device=dev)
         att = torch.empty((st.nnz, H), dtype=torch.float32, device=dev)   # output for training, scratch otherwise
-        plan, keep = st.plan_struct(st.plan.n_chunks * H * F * 4 if st.chunk_edges > 0 else 0)
+        plan, keep = st.plan_struct(max(st.plan.n_chunks * H * F * 4, _es_scratch(st, H)) if st.chunk_edges > 0 else 0)
         _cabi.call("cogdl_b200_gat_fwd_f32", _ptr(st.rowptr), _ptr(st.colind), _ptr(h_l), _ptr(h_r), _ptr(feat),
                    float(slope), _ptr(out), _ptr(att), st.n_rows, H, F, plan, _stream(dev))
         del keep
     return out, att
+
+
+def gat_attn_bwd_raw(st: CSRStructure, att, d_att, h_l, h_r, slope):
+    """(d_edge [nnz,H], g_row [n_rows,H]): softmax backward * LeakyReLU' and its row sums in one pass."""
+    dev = require_cuda(att, d_att, h_l, h_r)
+    att, d_att, h_l, h_r = _f32c(att, "att"), _f32c(d_att, "d_att"), _f32c(h_l, "attn_row"), _f32c(h_r, "attn_col")
+    H = att.shape[1]
+    with torch.cuda.device(dev):
+        d_edge = torch.empty_like(att)
+        g_row = torch.empty((st.n_rows, H), dtype=torch.float32, device=dev)
+        plan, keep = st.plan_struct(_es_scratch(st, H))
+        _cabi.call("cogdl_b200_gat_attn_bwd_f32", _ptr(st.rowptr), _ptr(st.colind), _ptr(att), _ptr(d_att), _ptr(h_l),
+                   _ptr(h_r), float(slope), _ptr(d_edge), _ptr(g_row), st.n_rows, H, plan, _stream(dev))
+        del keep
+    return d_edge, g_row
+
+
+def edge_colsum_raw(st_t: CSRStructure, perm, e):
+    """out[j,h] = sum of e[p,h] over the edges p whose column is j (st_t = cached transpose, perm its permutation)."""
+    dev = require_cuda(perm, e)
+    e = _f32c(e, "edge values")
+    H = e.shape[1]
+    with torch.cuda.device(dev):
+        out = torch.empty((st_t.n_rows, H), dtype=torch.float32, device=dev)
+        plan, keep = st_t.plan_struct(st_t.plan.n_chunks * H * 4 if st_t.chunk_edges > 0 else 0)
+        _cabi.call("cogdl_b200_edge_colsum_f32", _ptr(st_t.rowptr), _ptr(perm), _ptr(e), _ptr(out), st_t.n_rows, H, plan,
+                   _stream(dev))
+        del keep
+    return out

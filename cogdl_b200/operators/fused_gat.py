@@ -9,7 +9,7 @@ signature compatibility; the transpose comes from the cached structure.
 import torch
 
 from ..structure import structure_for, CSRStructure
-from ._raw import gat_fwd_raw, mhspmm_raw, mhsddmm_raw, edge_softmax_bwd_raw
+from ._raw import gat_fwd_raw, mhspmm_raw, mhsddmm_raw, gat_attn_bwd_raw, edge_colsum_raw
 
 
 class FusedGATFunction(torch.autograd.Function):
@@ -25,23 +25,20 @@ class FusedGATFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        """Native backward (precedent dgNN fused_gatconv_kernel.cu:636-790), five library calls, no eager
+        index arithmetic:  d feat = CSC mh-SpMM (perm fused) . d att = mh-SDDMM . (d edge, g_row) = softmax
+        backward * LeakyReLU' + row sums in one pass (cogdl_b200_gat_attn_bwd_f32) . g_col = column sums of
+        d edge through the cached transpose (cogdl_b200_edge_colsum_f32)."""
         attn_row, attn_col, feat, att = ctx.saved_tensors
         st = ctx.st
         grad_out = grad_out.contiguous()
         st_t, perm = st.csc()
-        H = att.shape[1]
-        grad_feat = mhspmm_raw(st_t, att, grad_out, perm=perm)            # [N,H,F]
-        grad_att = mhsddmm_raw(st, grad_out, feat)                        # [E,H]
-        grad_e = edge_softmax_bwd_raw(st, att, grad_att)                  # d/d leakyrelu output
-        # leakyrelu'(z) with z = attn_row[row] + attn_col[col]: recompute the sign from the inputs
-        rows = torch.repeat_interleave(torch.arange(st.n_rows, device=att.device),
-                                       (st.rowptr[1:] - st.rowptr[:-1]).long())
-        z = attn_row[rows] + attn_col[st.colind.long()]
-        grad_z = torch.where(z > 0, grad_e, grad_e * ctx.slope).contiguous()
-        ones = torch.ones((st.n_cols, H, 1), dtype=torch.float32, device=att.device)
-        g_row = mhspmm_raw(st, grad_z, ones[: st.n_cols]).view(st.n_rows, H)       # sum over a row's edges
-        g_col = mhspmm_raw(st_t, grad_z, torch.ones((st.n_rows, H, 1), dtype=torch.float32, device=att.device),
-                           perm=perm).view(st.n_cols, H)                          # sum over a column's edges
+        grad_feat = mhspmm_raw(st_t, att, grad_out, perm=perm) if ctx.needs_input_grad[7] else None
+        g_row = g_col = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            grad_att = mhsddmm_raw(st, grad_out, feat)                        # [E,H]
+            d_edge, g_row = gat_attn_bwd_raw(st, att, grad_att, attn_row, attn_col, ctx.slope)
+            g_col = edge_colsum_raw(st_t, perm, d_edge)
         return g_row, g_col, None, None, None, None, None, grad_feat
 
 

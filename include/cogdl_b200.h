@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define COGDL_B200_ABI_VERSION 3
+#define COGDL_B200_ABI_VERSION 4
 
 #define COGDL_B200_OK 0
 #define COGDL_B200_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
@@ -197,6 +197,10 @@ COGDL_B200_API int cogdl_b200_gather_rows_f32(const int32_t *perm, const float *
  * fwd: out = exp(in - max_row) / sum_row exp(in - max_row).  bwd: gin = y * (g - sum_row y*g).
  * Degree-0 rows own no entries, so nothing is written for them.
  * ------------------------------------------------------------------------------------- */
+/* With a hub plan that has hub rows, the calls below (and the GAT attention stages) need per-call scratch
+ * in plan->partials: at least cogdl_b200_edge_softmax_scratch_bytes(plan->n_chunks, H) bytes (per hub
+ * chunk and head: a (max, sum) pair for the two-pass split-row softmax + one partial row sum). */
+COGDL_B200_API int64_t cogdl_b200_edge_softmax_scratch_bytes(int64_t n_chunks, int64_t H);
 COGDL_B200_API int cogdl_b200_edge_softmax_fwd_f32(const int32_t *rowptr, const float *in, float *out,
                                     int64_t n_rows, int64_t H,
                                     const cogdl_b200_hub_plan_t *plan, cogdl_b200_stream_t stream);
@@ -256,6 +260,23 @@ COGDL_B200_API int cogdl_b200_gat_fwd_f32(const int32_t *rowptr, const int32_t *
                            const float *h_r, const float *feat, float negative_slope, float *out,
                            float *att_out, int64_t n_rows, int64_t H, int64_t F,
                            const cogdl_b200_hub_plan_t *plan, cogdl_b200_stream_t stream);
+
+/* GAT attention backward (autograd of cogdl/layers/gat_layer.py:73-74, precedent
+ * third_party/dgNN/dgNN/src/fused_gatconv/fused_gatconv_kernel.cu:636-790): softmax backward, LeakyReLU'
+ * and the row sums in ONE pass over the edge-aligned tensors --
+ *   d_edge[p,h] = att*(d_att - sum_row att*d_att) * leakyrelu'(h_l[row,h] + h_r[col,h])   [nnz,H]
+ *   g_row[i,h]  = sum_{p in row i} d_edge[p,h]                                            [n_rows,H]
+ * d_att is the multi-head SDDMM of (d out, feat).  g_col = cogdl_b200_edge_colsum_f32 over the transpose.
+ * Scratch in plan->partials as for the edge softmax. */
+COGDL_B200_API int cogdl_b200_gat_attn_bwd_f32(const int32_t *rowptr, const int32_t *colind, const float *att,
+                                const float *d_att, const float *h_l, const float *h_r, float negative_slope,
+                                float *d_edge, float *g_row, int64_t n_rows, int64_t H,
+                                const cogdl_b200_hub_plan_t *plan, cogdl_b200_stream_t stream);
+/* out[j,h] = sum_{q in column j of the transpose} e[perm[q], h]: column sums of an edge-aligned [nnz,H]
+ * tensor through the cached CSC (colptr, perm).  Deterministic (no atomics; hub columns via the plan's chunks). */
+COGDL_B200_API int cogdl_b200_edge_colsum_f32(const int32_t *colptr, const int32_t *perm, const float *e, float *out,
+                               int64_t n_cols, int64_t H, const cogdl_b200_hub_plan_t *plan /* of the transpose; scratch n_chunks*H*4 B */,
+                               cogdl_b200_stream_t stream);
 
 /* Device COO -> CSR (stable): row_ptr[num_nodes+1] and reindex[nnz] (CSR slot -> COO position),
  * int64 as cogdl.data.Graph stores them.

@@ -255,3 +255,18 @@ def subgraph(indptr, indices, node_idx):
     ne = f(_p(indptr, _i64p), _p(indices, _i64p), _p(node_idx, _i64p), _i64(ns), _i64(n), _p(out_indptr, _i64p),
            _p(out_indices, _i64p), _p(out_edges, _i64p))
     return out_indptr, out_indices[:ne].copy(), out_edges[:ne].copy()
+
+
+def gat_attn_bwd(rowptr, colind, att, d_att, h_l, h_r, slope=0.2, n_cols=None):
+    """(d_edge [nnz,H], g_row [n,H], g_col [n_cols,H]) -- autograd of gat_layer.py:73-74, see oracle.c."""
+    rowptr, colind = _a(rowptr, np.int32), _a(colind, np.int32)
+    att, d_att, h_l, h_r = _a(att, np.float32), _a(d_att, np.float32), _a(h_l, np.float32), _a(h_r, np.float32)
+    n, H = rowptr.shape[0] - 1, att.shape[1]
+    n_cols = h_r.shape[0] if n_cols is None else n_cols
+    d_edge = np.zeros_like(att)
+    g_row = np.zeros((n, H), np.float32)
+    g_col = np.zeros((n_cols, H), np.float32)
+    lib().oracle_gat_attn_bwd_f32(_p(rowptr, _i32p), _p(colind, _i32p), _p(att, _f32p), _p(d_att, _f32p), _p(h_l, _f32p),
+                                  _p(h_r, _f32p), ctypes.c_float(slope), _p(d_edge, _f32p), _p(g_row, _f32p),
+                                  _p(g_col, _f32p), _i64(n), _i64(n_cols), _i64(H))
+    return d_edge, g_row, g_col

@@ -446,3 +446,37 @@ ORACLE_API int64_t oracle_subgraph(const int64_t *indptr, const int64_t *indices
   free(assoc);
   return n_edges;
 }
+
+/* ------------------------------------------------------------------------
+ * GAT attention backward (the autograd of cogdl/layers/gat_layer.py:73-74 written out; the reference
+ * gets it from PyTorch autograd over h_l[row] + h_r[col] -> LeakyReLU -> edge_softmax):
+ *   s[i,h]      = sum_{p in row i} att[p,h] * d_att[p,h]          (edge_softmax.cu:63-98)
+ *   d_edge[p,h] = att[p,h] * (d_att[p,h] - s) * (z > 0 ? 1 : slope),  z = h_l[row,h] + h_r[col,h]
+ *   g_row[i,h]  = sum_{p in row i} d_edge[p,h];   g_col[j,h] = sum_{p: col[p] = j} d_edge[p,h]
+ * fp64 inside, rounded once.
+ * ---------------------------------------------------------------------- */
+ORACLE_API void oracle_gat_attn_bwd_f32(const int32_t *rowptr, const int32_t *colind, const float *att,
+                                        const float *d_att, const float *h_l, const float *h_r, float slope,
+                                        float *d_edge, float *g_row, float *g_col, int64_t n_rows,
+                                        int64_t n_cols, int64_t H) {
+  double *gc = (double *)calloc((size_t)(n_cols * H > 0 ? n_cols * H : 1), sizeof(double));
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const int32_t lb = rowptr[i], hb = rowptr[i + 1];
+    for (int64_t h = 0; h < H; ++h) {
+      double s = 0.0;
+      for (int32_t p = lb; p < hb; ++p) s += (double)att[(int64_t)p * H + h] * (double)d_att[(int64_t)p * H + h];
+      double gr = 0.0;
+      for (int32_t p = lb; p < hb; ++p) {
+        const int64_t k = (int64_t)p * H + h;
+        const float z = h_l[i * H + h] + h_r[(int64_t)colind[p] * H + h];
+        const double v = (double)att[k] * ((double)d_att[k] - s) * (z > 0.0f ? 1.0 : (double)slope);
+        d_edge[k] = (float)v;
+        gr += v;
+        gc[(int64_t)colind[p] * H + h] += v;
+      }
+      g_row[i * H + h] = (float)gr;
+    }
+  }
+  for (int64_t t = 0; t < n_cols * H; ++t) g_col[t] = (float)gc[t];
+  free(gc);
+}

@@ -193,15 +193,52 @@ def test_edge_softmax_fwd_bwd(dev, name, H):
     g = rng.standard_normal((ci.shape[0], H)).astype(np.float32)
     yref = oracle.edge_softmax_fwd(rp, e)
     gref = oracle.edge_softmax_bwd(rp, yref, g)
-    st = structure(rp, ci, n_cols, dev)
-    y = edge_softmax_fwd_raw(st, T(e, dev))
-    gin = edge_softmax_bwd_raw(st, T(yref, dev), T(g, dev))
-    assert rel(y.cpu().numpy(), yref) <= TOL
-    assert rel(gin.cpu().numpy(), gref) <= TOL
-    if ci.shape[0]:
-        # rows sum to one per head
-        seg = np.add.reduceat(y.cpu().numpy(), rp[:-1][np.diff(rp) > 0], axis=0)
-        assert np.allclose(seg, 1.0, atol=1e-5)
+    # chunk 256: tiles of 2048 floats or the warp kernel (H >= 16); 64 / 16: the 512- and 1024-float tiles,
+    # many chunks per hub row (split-row statistics), cp.async.bulk staging when H % 4 == 0; 0: no plan
+    for chunk in (256, 64, 16, 0):
+        st = structure(rp, ci, n_cols, dev, chunk)
+        y = edge_softmax_fwd_raw(st, T(e, dev))
+        gin = edge_softmax_bwd_raw(st, T(yref, dev), T(g, dev))
+        assert rel(y.cpu().numpy(), yref) <= TOL, chunk
+        assert rel(gin.cpu().numpy(), gref) <= TOL, chunk
+        if ci.shape[0]:
+            # rows sum to one per head
+            seg = np.add.reduceat(y.cpu().numpy(), rp[:-1][np.diff(rp) > 0], axis=0)
+            assert np.allclose(seg, 1.0, atol=1e-5)
+        if chunk:
+            assert int(st.plan.counters.abs().sum()) == 0   # arrival counters left clean by both passes
+        # unaligned views (offset by one float): the bulk path must be refused, results unchanged
+        if H % 4 == 0 and ci.shape[0]:
+            buf = torch.empty(e.size + 1, device=dev)
+            ev = buf[1:].view(e.shape)
+            ev.copy_(T(e, dev))
+            assert torch.equal(edge_softmax_fwd_raw(st, ev), y) or rel(edge_softmax_fwd_raw(st, ev).cpu().numpy(), yref) <= TOL
+
+
+@pytest.mark.parametrize("name", ["tiny", "ragged", "hub", "two_hubs", "empty_graph"])
+@pytest.mark.parametrize("H", [8, 1, 4, 16, 3])
+def test_gat_attention_backward_and_colsum(dev, name, H):
+    """cogdl_b200_gat_attn_bwd_f32 + cogdl_b200_edge_colsum_f32 against the oracle's written-out autograd."""
+    from cogdl_b200.operators._raw import gat_attn_bwd_raw, edge_colsum_raw
+
+    rp, ci, n_cols = case(name)
+    if n_cols != rp.shape[0] - 1:
+        pytest.skip("square graphs only (h_l / h_r share the node set)")
+    n = rp.shape[0] - 1
+    rng = np.random.default_rng(21)
+    att = oracle.edge_softmax_fwd(rp, np.clip(rng.standard_normal((ci.shape[0], H)) * 2, -8, 8).astype(np.float32))
+    d_att = rng.standard_normal((ci.shape[0], H)).astype(np.float32)
+    hl, hr = rng.standard_normal((n, H)).astype(np.float32), rng.standard_normal((n, H)).astype(np.float32)
+    de_ref, gr_ref, gc_ref = oracle.gat_attn_bwd(rp, ci, att, d_att, hl, hr, 0.2)
+    for chunk in (256, 16, 0):
+        st = structure(rp, ci, n_cols, dev, chunk)
+        de, gr = gat_attn_bwd_raw(st, T(att, dev), T(d_att, dev), T(hl, dev), T(hr, dev), 0.2)
+        assert rel(de.cpu().numpy(), de_ref) <= TOL and rel(gr.cpu().numpy(), gr_ref) <= TOL, chunk
+        st_t, perm = st.csc()
+        gc = edge_colsum_raw(st_t, perm, de)
+        assert rel(gc.cpu().numpy(), gc_ref) <= TOL, chunk
+        gc2 = edge_colsum_raw(st_t, perm, de)
+        assert torch.equal(gc, gc2)            # deterministic
 
 
 # ------------------------------------------------------------------------------------ multi-head
