@@ -11,6 +11,11 @@ rebinds the dispatch functions inside every imported cogdl module to the sm_100a
 CPU tensors), then install(), then a NEW model with the same state_dict on CUDA.  Logits and every
 parameter gradient must agree within 1e-4 (relative to the tensor's scale: cuBLAS fp32 GEMMs sit
 upstream of the sparse ops, and the reference's CPU edge-softmax is a different algorithm).
+GAT gradients are the exception: the reference's CPU edge-softmax fallback computes its denominator with
+the non-differentiable CPU SpMM extension (spmm_utils.py:149-169: `node_sum = spmm(graph, ones)`), so its
+CPU backward silently drops the -y*sum(y*g) term -- 70 % off in W, see the assertion below.  The yardstick
+for GAT gradients is therefore a plain-torch fp64 restatement of GATLayer (gat_layer.py:59-86) with exact
+autograd; the reference CPU run still pins the logits.
 aggr="max" has NO CPU implementation in the reference (scatter_max is CUDA-only), so that model is
 compared with a plain-torch restatement of SAGELayer's arithmetic using the model's own weights.
 """
@@ -30,6 +35,29 @@ TOL = 1e-4
 def rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def gat_exact_grads(state, graph, target, nhead=8, slope=0.2):
+    """2-layer reference GAT (gat.py:54-103, GATLayer gat_layer.py:59-86, dropout 0) restated with dense torch
+    ops in fp64: logits and exact parameter gradients of the cross-entropy."""
+    row, col = graph.edge_index
+    n = graph.num_nodes
+    p = {k: v.detach().double().clone().requires_grad_(True) for k, v in state.items()}
+
+    def layer(x, W, al, ar, H):
+        h = (x @ W).view(n, H, -1)
+        hl, hr = (al * h).sum(-1), (ar * h).sum(-1)
+        e = torch.nn.functional.leaky_relu(hl[row] + hr[col], slope)
+        m = torch.full((n, H), -1e300, dtype=torch.float64).scatter_reduce(0, row[:, None].expand(-1, H), e, "amax")
+        ex = torch.exp(e - m[row])
+        a = ex / torch.zeros(n, H, dtype=torch.float64).index_add(0, row, ex)[row]
+        return torch.zeros_like(h).index_add(0, row, a[:, :, None] * h[col]).view(n, -1)
+
+    x = graph.x.double()
+    x = torch.nn.functional.elu(layer(x, p["attentions.0.W"], p["attentions.0.a_l"], p["attentions.0.a_r"], nhead))
+    out = layer(x, p["attentions.1.W"], p["attentions.1.a_l"], p["attentions.1.a_r"], 1)
+    torch.nn.functional.cross_entropy(out, target).backward()
+    return out.detach(), {k: v.grad for k, v in p.items()}
 
 
 def cora_shaped_graph(Graph, n=2708, e=5278, feats=64, seed=0):
@@ -88,6 +116,12 @@ def ref():
         model.train()
         out, grads = run(model, copy.deepcopy(g_cpu), fwd)
         runs[name] = {"state": copy.deepcopy(model.state_dict()), "out": out, "grads": grads, "make": make, "fwd": fwd}
+    # GAT: exact gradients (see the module docstring) + the evidence that the reference CPU backward is not exact
+    ex_out, ex_grads = gat_exact_grads(runs["gat"]["state"], g_cpu, target)
+    assert rel(runs["gat"]["out"], ex_out) <= 1e-5
+    assert rel(runs["gat"]["grads"]["attentions.0.W"], ex_grads["attentions.0.W"]) > 0.1, \
+        "the reference CPU GAT backward was expected to be inexact (detached softmax denominator)"
+    runs["gat"]["grads"] = ex_grads
     # ---------------- phase 2: install the sm_100a backend into the reference package
     import cogdl_b200
 
