@@ -60,6 +60,12 @@ struct EsParams {
   bool bulk;              // tiles may be moved with cp.async.bulk (alignment checked on the host)
 };
 
+// exp for the plan-based kernels: arguments are x - max <= 0.  ex2.approx(x * log2 e): 2 ulp from the MUFU plus
+// |x| * 2^-24 from the scaling product, i.e. <= ~2e-6 relative for logits within 30 of the row maximum and an
+// absolute error far below 1e-5 of the row's largest term beyond that (parity bar: 1e-5).  FMUL + MUFU.EX2
+// instead of the ~12-instruction expf(): these kernels are issue-bound, not memory-bound (ncu, profiles/).
+__device__ __forceinline__ float es_exp(float x) { return __expf(x); }
+
 // reduce across lanes that share lane % H  (strides 16 .. H)
 __device__ __forceinline__ float head_max(float v, int H) {
   for (int s = 16; s >= H; s >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, s));
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(256) es_stats_kernel(const EsParams p) {
     const float hl = (MODE == 2) ? __ldg(p.a + (int64_t)w.row * H + head) : 0.f;
     for (int t = lane; t < n; t += 32) m = fmaxf(m, es_in<MODE>(p, w.lb, t, head, hl));
     m = head_max(m, H);
-    for (int t = lane; t < n; t += 32) s += expf(es_in<MODE>(p, w.lb, t, head, hl) - m);   // second read hits L1
+    for (int t = lane; t < n; t += 32) s += es_exp(es_in<MODE>(p, w.lb, t, head, hl) - m);   // second read hits L1
     s = head_sum(s, H);
   }
   if (lane < H) {
@@ -197,16 +203,23 @@ __global__ void __launch_bounds__(256) es_stats_kernel(const EsParams p) {
     // lanes sharing a head split the chunks between them, then merge across the head's lanes
     const int grp = lane >> p.lgH, ngrp = 32 >> p.lgH;
     float M = -CUDART_INF_F, S = 0.f;
-    for (int q = grp; q < w.n_row_chunks; q += ngrp) {
-      float cm, cs;
-      const float2 *src = p.stats + (int64_t)(w.first + q) * H + head;
-      asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(cm), "=f"(cs) : "l"(src));
-      if (MODE == 1 || MODE == 3) {
-        S += cs;
-      } else {
-        const float nm = fmaxf(M, cm);
-        S = S * expf(M - nm) + cs * expf(cm - nm);   // exp(-inf) = 0 on the first chunk
-        M = nm;
+    const float2 *sb = p.stats + (int64_t)w.first * H + head;
+    for (int q0 = grp; q0 < w.n_row_chunks; q0 += 4 * ngrp) {
+      float2 c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {        // four independent L2 loads in flight (the 22 K-edge hub merges 354 chunks)
+        const int q = q0 + u * ngrp;
+        c[u] = (q < w.n_row_chunks) ? __ldcg(sb + (int64_t)q * H) : make_float2(-CUDART_INF_F, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (MODE == 1 || MODE == 3) {
+          S += c[u].y;
+        } else if (c[u].x != -CUDART_INF_F) {
+          const float nm = fmaxf(M, c[u].x);
+          S = S * es_exp(M - nm) + c[u].y * es_exp(c[u].x - nm);   // exp(-inf) = 0 on the first chunk
+          M = nm;
+        }
       }
     }
     for (int st = 16; st >= H; st >>= 1) {
@@ -215,8 +228,8 @@ __global__ void __launch_bounds__(256) es_stats_kernel(const EsParams p) {
         S += oS;
       } else {
         const float nm = fmaxf(M, oM);
-        const float a = (M == -CUDART_INF_F) ? 0.f : S * expf(M - nm);
-        const float b = (oM == -CUDART_INF_F) ? 0.f : oS * expf(oM - nm);
+        const float a = (M == -CUDART_INF_F) ? 0.f : S * es_exp(M - nm);
+        const float b = (oM == -CUDART_INF_F) ? 0.f : oS * es_exp(oM - nm);
         S = a + b;
         M = nm;
       }
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32) es_main_kernel(const EsParams p) {
       const float hl = (MODE == 2) ? __ldg(p.a + (int64_t)w.row * H + head) : 0.f;
       const float inv = 1.f / rs.y;
 #pragma unroll 4
-      for (int t = lane; t < n; t += 32) st_stream(o + t, expf(es_in<MODE>(p, w.lb, t, head, hl) - rs.x) * inv);
+      for (int t = lane; t < n; t += 32) st_stream(o + t, es_exp(es_in<MODE>(p, w.lb, t, head, hl) - rs.x) * inv);
     }
     return;
   }
@@ -425,7 +438,7 @@ __global__ void __launch_bounds__(WARPS * 32) es_main_kernel(const EsParams p) {
           for (int k = k0; k < k1; ++k) mx = fmaxf(mx, T[k * H + h]);
           float s = 0.f;
           for (int k = k0; k < k1; ++k) {
-            const float ex = expf(T[k * H + h] - mx);
+            const float ex = es_exp(T[k * H + h] - mx);
             T[k * H + h] = ex;
             s += ex;
           }
