@@ -372,6 +372,24 @@ __global__ void __launch_bounds__(256) spmm_half_kernel(const SpmmHalfParams p) 
   }
 }
 
+// Only the hub rows (degree > plan chunk) of Y = A @ X: the hub-chunk items of the row-stream kernel with
+// their in-order combine, no segments.  Used by the fused GCN layer (fused_gcn.cu), which aggregates every
+// other row straight into shared memory.  F % 4 == 0, 16-byte aligned X / Y.
+int spmm_hub_rows_only(const int32_t *rowptr, const int32_t *colind, const float *val, const float *X, float *Y,
+                       int64_t F, const cogdl_b200_hub_plan_t *plan, cudaStream_t stream) {
+  SpmmParams p;
+  p.rowptr = rowptr; p.colind = colind; p.val = val; p.X0 = X; p.X1 = X; p.n0 = INT64_MAX; p.Y = Y; p.n_rows = 0;
+  p.hub = hub_view(plan);
+  p.hub.n_segs = 0;
+  p.n_peers = 0; p.peer_shift = 0;
+  for (int i = 0; i < 8; ++i) p.peers[i] = nullptr;
+  p.FV = (int)(F / 4);
+  if (p.hub.n_chunks == 0) return COGDL_B200_OK;
+  const StreamParams q = to_stream(p);
+  if (p.FV <= 32) return launch_stream<float4, 1, 4, 5, false>(q, val ? MODE_WEIGHTED : MODE_UNWEIGHTED, stream);
+  return launch_stream<float4, 2, 4, 1>(q, val ? MODE_WEIGHTED : MODE_UNWEIGHTED, stream);
+}
+
 }  // namespace cogdl_b200
 
 using namespace cogdl_b200;

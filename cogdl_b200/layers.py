@@ -35,9 +35,15 @@ def _norm(name, channels):
 
 
 class GCNLayer(nn.Module):
-    def __init__(self, in_features, out_features, dropout=0.0, activation=None, residual=False, norm=None, bias=True):
+    """fused=True (opt-in): (A.X).W^T + (A.1) b^T with the dense transform and ReLU in the epilogue of the
+    aggregation kernel (tcgen05, cogdl_b200/csrc/fused_gcn.cu) instead of the reference order A.(X.W^T + b);
+    taken when in_features == 128, out_features <= 128 and there is no norm layer between them."""
+
+    def __init__(self, in_features, out_features, dropout=0.0, activation=None, residual=False, norm=None, bias=True,
+                 fused=False):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
+        self.fused, self._act_name = bool(fused), activation
         self.linear = nn.Linear(in_features, out_features, bias=bias)
         self.dropout = nn.Dropout(dropout) if dropout > 0 else None
         self.residual = nn.Linear(in_features, out_features) if residual else None
@@ -47,11 +53,20 @@ class GCNLayer(nn.Module):
         nn.init.uniform_(self.linear.weight, -stdv, stdv)
 
     def forward(self, graph, x):
-        out = spmm(graph, self.linear(x))      # dense first, then aggregate (gcn_layer.py:52-53)
-        if self.norm is not None:
-            out = self.norm(out)
-        if self.act is not None:
-            out = self.act(out)
+        from .operators import fused_gcn
+
+        if (self.fused and self.norm is None and x.is_cuda and x.dtype == torch.float32 and graph.out_norm is None
+                and graph.in_norm is None and fused_gcn.supported(self.in_features, self.out_features)):
+            relu = self._act_name == "relu"
+            out = fused_gcn.fused_gcn_layer(graph, x, self.linear.weight, self.linear.bias, relu=relu)
+            if self.act is not None and not relu:
+                out = self.act(out)
+        else:
+            out = spmm(graph, self.linear(x))      # dense first, then aggregate (gcn_layer.py:52-53)
+            if self.norm is not None:
+                out = self.norm(out)
+            if self.act is not None:
+                out = self.act(out)
         if self.residual is not None:
             out = out + self.residual(x)
         if self.dropout is not None:

@@ -1,0 +1,109 @@
+"""Fused GCN layer: act((A.X).W^T + (A.1) b^T) in one kernel with a tcgen05 GEMM epilogue.
+
+Mathematically the reference layer `act(spmm(graph, linear(x)))` (cogdl/layers/gcn_layer.py:51-64; the bias
+is added BEFORE the aggregation there, hence the (A.1) b^T term), re-associated -- so it is opt-in
+(`GCNLayer(..., fused=True)` in cogdl_b200.layers, or call `fused_gcn_layer` directly) and is held to 1e-5
+against an fp64 evaluation instead of being bit-matched.  Kernel: cogdl_b200/csrc/fused_gcn.cu.
+"""
+import torch
+
+from .. import _cabi
+from ..structure import CSRStructure, _ptr, _stream, require_cuda
+from ._raw import spmm_raw
+
+
+def supported(K, Fout):
+    return bool(_cabi.load().cogdl_b200_gcn_fused_supported(int(K), int(Fout)))
+
+
+def fused_gcn_raw(st: CSRStructure, val, x, weight, bias=None, relu=False):
+    """x [n_src,128] fp32, weight [Fout,128] (nn.Linear layout), bias [Fout] | None -> [n_rows, Fout]."""
+    dev = require_cuda(x, weight, val, bias)
+    if x.dtype != torch.float32 or weight.dtype != torch.float32:
+        raise TypeError("fused_gcn_raw: float32 only")
+    x, weight = x.contiguous(), weight.contiguous()
+    K, Fout = x.shape[1], weight.shape[0]
+    if weight.shape[1] != K or not supported(K, Fout):
+        raise ValueError(f"fused GCN layer needs in_features == 128 and out_features <= 128, got {K} -> {Fout}")
+    val = None if val is None else val.contiguous().view(-1).float()
+    bias = None if bias is None else bias.contiguous().float()
+    with torch.cuda.device(dev):
+        out = torch.empty((st.n_rows, Fout), dtype=torch.float32, device=dev)
+        plan, keep = st.plan_struct(st.plan.n_chunks * K * 4)
+        hub = torch.empty((st.n_rows, K), dtype=torch.float32, device=dev) if st.plan.n_chunks > 0 else None
+        _cabi.call("cogdl_b200_gcn_fused_f32", _ptr(st.rowptr), _ptr(st.colind), _ptr(val), _ptr(x), _ptr(weight), _ptr(bias),
+                   _ptr(out), _ptr(hub), st.n_rows, K, Fout, int(bool(relu)), plan, _stream(dev))
+        del keep, hub
+    return out
+
+
+class FusedGCNFunction(torch.autograd.Function):
+    """Forward: the fused kernel.  Backward (training): with G' = dOUT * relu'(OUT),
+       dW = G'^T (A.X)   db = G'^T (A.1)   dX = A^T (G' W)        -- A.X is recomputed by one SpMM (it was never
+       written in the forward), the dense products are plain library GEMMs (cuBLAS via torch.matmul)."""
+
+    @staticmethod
+    def forward(ctx, st, val, x, weight, bias, relu, sym):
+        out = fused_gcn_raw(st, val, x, weight, bias, relu)
+        ctx.st, ctx.relu, ctx.sym = st, bool(relu), bool(sym)
+        ctx.save_for_backward(val, x, weight, bias, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        val, x, weight, bias, out = ctx.saved_tensors
+        st = ctx.st
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[3] or (bias is not None and ctx.needs_input_grad[4]):
+            ax = spmm_raw(st, val, x)
+            if ctx.needs_input_grad[3]:
+                gw = g.t() @ ax
+            if bias is not None and ctx.needs_input_grad[4]:
+                ones = torch.ones((x.shape[0], 4), device=x.device)
+                gb = g.t() @ spmm_raw(st, val, ones)[:, 0]
+        if ctx.needs_input_grad[2]:
+            gwm = (g @ weight).contiguous()
+            if ctx.sym:
+                gx = spmm_raw(st, val, gwm)
+            else:
+                from ._raw import gather_rows_raw
+
+                st_t, perm = st.csc()
+                gx = spmm_raw(st_t, None if val is None else gather_rows_raw(perm, val), gwm)
+        return None, None, gx, gw, gb, None, None
+
+
+def fused_gcn_layer(graph, x, weight, bias=None, relu=False):
+    """graph: cogdl_b200.Graph or a real cogdl.data.Graph (same attribute surface as spmm())."""
+    from ..utils.spmm_utils import _structure
+
+    if graph.out_norm is not None or graph.in_norm is not None:
+        raise NotImplementedError("fused GCN layer: graphs with separate in/out norms take the unfused path")
+    return FusedGCNFunction.apply(_structure(graph), graph.raw_edge_weight, x, weight, bias, relu, graph.is_symmetric())
+
+
+def bench_fused_vs_unfused(torch_mod, st, w, x, bench):
+    """bench.py extras: one GCN layer 128 -> 128 (+bias, ReLU) on the arxiv shape, fused vs SpMM + cuBLAS."""
+    dev = x.device
+    lin = torch_mod.nn.Linear(128, 128).to(dev)
+    W, b = lin.weight.detach().contiguous(), lin.bias.detach().contiguous()
+    res = {}
+
+    def unfused_ref_order():       # the reference order: GEMM (+bias) first, then aggregate, then ReLU
+        return torch_mod.relu_(spmm_raw(st, w, torch_mod.addmm(b, x, W.t())))
+
+    def unfused_same_order():      # aggregate first, then GEMM + bias * rowsum + ReLU in torch
+        return torch_mod.relu_(spmm_raw(st, w, x) @ W.t())
+
+    bench("C2_gcn_layer_fused_tcgen05", lambda: fused_gcn_raw(st, w, x, W, b, True))
+    bench("C2_gcn_layer_unfused_gemm_then_spmm", unfused_ref_order)
+    bench("C2_gcn_layer_unfused_spmm_then_gemm", unfused_same_order)
+    a = fused_gcn_raw(st, w, x, W, b, True).double()
+    r = torch_mod.relu(torch_mod.sparse_csr_tensor(st.rowptr.long(), st.colind.long(), w.double(), size=(st.n_rows, st.n_cols))
+                       @ (x.double() @ W.double().t() + b.double()))
+    scale = torch_mod.maximum(r.abs(), r.abs().amax(dim=1, keepdim=True)).clamp_min(1e-30)
+    res["C2_gcn_layer_fused_max_rel_err_vs_fp64"] = float(((a - r).abs() / scale).max())
+    return res

@@ -278,6 +278,23 @@ COGDL_B200_API int cogdl_b200_edge_colsum_f32(const int32_t *colptr, const int32
                                int64_t n_cols, int64_t H, const cogdl_b200_hub_plan_t *plan /* of the transpose; scratch n_chunks*H*4 B */,
                                cogdl_b200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused GCN layer: OUT = act( (A.X).W^T + (A.1) b^T ), A = (rowptr, colind, val).
+ * Equal to the reference layer  act( A.(X.W^T + 1 b^T) )  (cogdl/layers/gcn_layer.py:51-64, bias inside the
+ * aggregation) up to fp32 rounding; the products are re-associated so the gather runs on the raw features
+ * and the dense transform runs on the aggregated 128-row tile while it is on chip: bf16x3-split operands
+ * (24 mantissa bits, six products), tcgen05.mma into TMEM, fp32 accumulate -- error vs fp64 ~1e-7 of the row
+ * scale.  X [n_src,K], W [Fout,K] (torch.nn.Linear.weight layout), bias [Fout] or NULL, out [n_rows,Fout].
+ * Needs K == 128, Fout <= 128 (cogdl_b200_gcn_fused_supported), a hub plan with edge_row, 16-byte aligned
+ * X / W / out.  hub_agg: scratch [n_rows, K] fp32, required iff the plan has hub rows (only those rows are
+ * written); plan->partials as for cogdl_b200_spmm_csr_f32 (n_chunks*K*4 bytes).
+ * ------------------------------------------------------------------------------------- */
+COGDL_B200_API int cogdl_b200_gcn_fused_supported(int64_t K, int64_t Fout);
+COGDL_B200_API int cogdl_b200_gcn_fused_f32(const int32_t *rowptr, const int32_t *colind, const float *val, const float *X,
+                             const float *W, const float *bias, float *out, float *hub_agg, int64_t n_rows,
+                             int64_t K, int64_t Fout, int32_t relu, const cogdl_b200_hub_plan_t *plan,
+                             cogdl_b200_stream_t stream);
+
 /* Device COO -> CSR (stable): row_ptr[num_nodes+1] and reindex[nnz] (CSR slot -> COO position),
  * int64 as cogdl.data.Graph stores them.
  * Replaces  sampler.coo2csr_cpu_index(row, col, num_nodes)   cogdl/operators/sample/sample.cpp:234-270

@@ -304,3 +304,34 @@ def test_sampler_generator_matches_between_library_and_oracle():
     lib = cogdl_b200._cabi.load()
     for seed, slot, k in ((0, 0, 0), (1, 2, 3), (2**63 + 5, 10**9, 77), (2**64 - 1, 2**40, 2**33)):
         assert int(lib.cogdl_b200_sample_draw(seed, slot, k)) == oracle.sample_draw(seed, slot, k)
+
+
+def test_bf16x3_split_gemm_numerics_emulated():
+    """The fused GCN layer (cogdl_b200/csrc/fused_gcn.cu) multiplies fp32 operands on the bf16 tensor cores by
+    splitting each into three bf16 terms and adding the six products of order <= 2^-16.  Emulated here in
+    numpy (bf16 rounding through torch): the error against fp64 must be at the 1e-7 level, i.e. well inside
+    the 1e-5 bar, while plain bf16 and the 3-term shortcut are not."""
+    rng = np.random.default_rng(0)
+
+    def bf16(x):
+        return torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+
+    def split3(x):
+        a1 = bf16(x)
+        r1 = (x - a1).astype(np.float32)
+        a2 = bf16(r1)
+        a3 = bf16((r1 - a2).astype(np.float32))
+        assert np.abs(x.astype(np.float64) - (a1.astype(np.float64) + a2 + a3)).max() <= 2.0 ** -22 * np.abs(x).max()
+        return a1, a2, a3
+
+    A = (rng.standard_normal((256, 128)) * rng.random((256, 1)) * 30).astype(np.float32)
+    W = (rng.standard_normal((128, 128)) / 11.3).astype(np.float32)
+    ref = A.astype(np.float64) @ W.T.astype(np.float64)
+    scale = np.maximum(np.abs(ref), np.abs(ref).max(1, keepdims=True))
+    As, Ws = split3(A), split3(W)
+    acc = np.zeros_like(ref, dtype=np.float32)
+    for i, j in [(2, 0), (1, 1), (0, 2), (1, 0), (0, 1), (0, 0)]:
+        acc = (acc + (As[i].astype(np.float64) @ Ws[j].T.astype(np.float64)).astype(np.float32)).astype(np.float32)
+    assert (np.abs(acc - ref) / scale).max() <= 5e-7
+    plain = bf16(A).astype(np.float64) @ bf16(W).T.astype(np.float64)
+    assert (np.abs(plain - ref) / scale).max() > 1e-4
