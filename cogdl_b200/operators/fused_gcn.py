@@ -27,6 +27,8 @@ def fused_gcn_raw(st: CSRStructure, val, x, weight, bias=None, relu=False):
         raise ValueError(f"fused GCN layer needs in_features == 128 and out_features <= 128, got {K} -> {Fout}")
     val = None if val is None else val.contiguous().view(-1).float()
     bias = None if bias is None else bias.contiguous().float()
+    if st.nnz == 0:        # no edge anywhere: A = 0, so (A.X).W^T + (A.1) b^T = 0 and act(0) = 0 for ReLU / identity
+        return torch.zeros((st.n_rows, Fout), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         out = torch.empty((st.n_rows, Fout), dtype=torch.float32, device=dev)
         plan, keep = st.plan_struct(st.plan.n_chunks * K * 4)
