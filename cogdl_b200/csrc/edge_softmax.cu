@@ -242,6 +242,49 @@ __global__ void __launch_bounds__(256) es_stats_kernel(const EsParams p) {
   }
 }
 
+// ---------------------------------------------------------------- hub chunk, pass 2 (shared by both main kernels)
+// normalise the chunk's elements with its row's merged statistics (stats[first slot])
+template <int MODE>
+__device__ __forceinline__ void es_chunk_item(const EsParams &p, int64_t item, int lane) {
+  constexpr bool TWO = (MODE == 1 || MODE == 3);
+  const int H = p.H;
+
+    const WorkItem w = decode_item(item, 0, p.rowptr, p.hub);
+    const int head = lane & (H - 1);
+    const int n = (w.hb - w.lb) * H;
+    const float2 rs = __ldg(p.stats + (int64_t)w.first * H + head);
+    float *o = p.out + (int64_t)w.lb * H;
+    if (TWO) {
+      const float *y = p.a + (int64_t)w.lb * H, *g = p.b + (int64_t)w.lb * H;
+      if (MODE == 1) {
+#pragma unroll 4
+        for (int t = lane; t < n; t += 32) st_stream(o + t, __ldg(y + t) * (__ldg(g + t) - rs.y));
+      } else {
+        const float hlrow = __ldg(p.hl + (int64_t)w.row * H + head);
+        float acc = 0.f;
+        for (int t = lane; t < n; t += 32) {
+          const float v = __ldg(y + t) * (__ldg(g + t) - rs.y) * es_dact(p, w.lb, t, head, hlrow);
+          st_stream(o + t, v);
+          acc += v;
+        }
+        acc = head_sum(acc, H);
+        if (lane < H) st_cg(p.part + (int64_t)w.slot * H + lane, acc);
+        if (hub_arrive_last<32>(w, p.hub, lane)) {      // row sum of the hub row: chunk partials in chunk order
+          if (lane < H) {
+            float tot = 0.f;
+            for (int q = 0; q < w.n_row_chunks; ++q) tot += ld_cg(p.part + (int64_t)(w.first + q) * H + lane);
+            p.grow[(int64_t)w.row * H + lane] = tot;
+          }
+        }
+      }
+    } else {
+      const float hl = (MODE == 2) ? __ldg(p.a + (int64_t)w.row * H + head) : 0.f;
+      const float inv = 1.f / rs.y;
+#pragma unroll 4
+      for (int t = lane; t < n; t += 32) st_stream(o + t, es_exp(es_in<MODE>(p, w.lb, t, head, hl) - rs.x) * inv);
+    }
+    }
+
 // ---------------------------------------------------------------- bulk-copy helpers (TMA 1-D)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -289,40 +332,7 @@ __global__ void __launch_bounds__(WARPS * 32) es_main_kernel(const EsParams p) {
 
   // ------------------------------------------------ hub chunk: normalise with the row's merged statistics
   if (item < p.hub.n_chunks) {
-    const WorkItem w = decode_item(item, 0, p.rowptr, p.hub);
-    const int head = lane & (H - 1);
-    const int n = (w.hb - w.lb) * H;
-    const float2 rs = __ldg(p.stats + (int64_t)w.first * H + head);
-    float *o = p.out + (int64_t)w.lb * H;
-    if (TWO) {
-      const float *y = p.a + (int64_t)w.lb * H, *g = p.b + (int64_t)w.lb * H;
-      if (MODE == 1) {
-#pragma unroll 4
-        for (int t = lane; t < n; t += 32) st_stream(o + t, __ldg(y + t) * (__ldg(g + t) - rs.y));
-      } else {
-        const float hlrow = __ldg(p.hl + (int64_t)w.row * H + head);
-        float acc = 0.f;
-        for (int t = lane; t < n; t += 32) {
-          const float v = __ldg(y + t) * (__ldg(g + t) - rs.y) * es_dact(p, w.lb, t, head, hlrow);
-          st_stream(o + t, v);
-          acc += v;
-        }
-        acc = head_sum(acc, H);
-        if (lane < H) st_cg(p.part + (int64_t)w.slot * H + lane, acc);
-        if (hub_arrive_last<32>(w, p.hub, lane)) {      // row sum of the hub row: chunk partials in chunk order
-          if (lane < H) {
-            float tot = 0.f;
-            for (int q = 0; q < w.n_row_chunks; ++q) tot += ld_cg(p.part + (int64_t)(w.first + q) * H + lane);
-            p.grow[(int64_t)w.row * H + lane] = tot;
-          }
-        }
-      }
-    } else {
-      const float hl = (MODE == 2) ? __ldg(p.a + (int64_t)w.row * H + head) : 0.f;
-      const float inv = 1.f / rs.y;
-#pragma unroll 4
-      for (int t = lane; t < n; t += 32) st_stream(o + t, es_exp(es_in<MODE>(p, w.lb, t, head, hl) - rs.x) * inv);
-    }
+    es_chunk_item<MODE>(p, item, lane);
     return;
   }
 
@@ -467,6 +477,209 @@ __global__ void __launch_bounds__(WARPS * 32) es_main_kernel(const EsParams p) {
   }
 }
 
+// ---------------------------------------------------------------- main kernel, register-resident segments
+// For tiles of <= KMAX * 32 floats (every H <= 16 with the default 64-edge chunks) nothing is staged at all:
+// lane L owns the window's elements L, L + 32, ... (fully coalesced 128-byte loads, all issued up front:
+// 2 * KMAX independent loads in flight per lane), i.e. ONE head (L % H) of every (32 / H)-th edge ("slot"
+// L / H).  Per-(row, head) reductions are two-level: each lane folds the run of its own elements that belong
+// to one row and drops one partial per (slot, row, head) into a small shared array (padded: conflict free);
+// a short (row, head)-per-lane pass folds the <= 32/H partials in slot order (deterministic) and leaves the
+// row statistic where every lane can read it.  All 32 lanes are busy whatever the degree distribution --
+// the staged kernel above gives one (row, head) pair to a lane, which on power-law rows is a 2-3x loss
+// (ncu, profiles/: 2.2 warp-instructions per element, issue-bound).  Results go straight to global memory.
+template <int MODE, int KMAX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (KMAX <= 16 ? 6 : 3)) es_reg_kernel(const EsParams p) {
+  constexpr bool TWO = (MODE == 1 || MODE == 3);
+  constexpr int CAP = KMAX * 32;
+  __shared__ float SLA_all[WARPS][33 * 32];    // partial per (slot, row, head): index (slot * 33 + row) * H + head
+  __shared__ float RS_all[WARPS][32 * 32];     // merged statistic per (row, head):  index row * H + head
+  __shared__ int RP_all[WARPS][34];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * WARPS + wib;
+  const int H = p.H, lgH = p.lgH;
+  if (item < p.hub.n_chunks) {
+    es_chunk_item<MODE>(p, item, lane);
+    return;
+  }
+  const int64_t seg = item - p.hub.n_chunks;
+  if (seg >= p.hub.n_segs) return;
+  const int2 rr = __ldg(p.hub.segs + seg);
+  float *SLA = SLA_all[wib], *RS = RS_all[wib];
+  int *RP = RP_all[wib];
+  const int h = lane & (H - 1), slot = lane >> lgH, S = 32 >> lgH;
+  int rw = rr.x;
+  while (rw < rr.y) {
+    const int row = rw + lane;
+    const int base = __ldg(p.rowptr + rw);
+    int endl = 0x7fffffff;
+    if (row < rr.y) endl = __ldg(p.rowptr + row + 1);
+    const unsigned fit = __ballot_sync(FULL, row < rr.y && (int64_t)(endl - base) * H <= CAP);
+    const int m = __popc(fit);
+    if (m == 0) {                              // cannot happen when chunk_edges * H <= CAP (host check)
+      rw += 1;
+      continue;
+    }
+    const int e_end = __shfl_sync(FULL, endl, m - 1);
+    const int n = (e_end - base) * H;
+    if (lane < m) RP[lane + 1] = endl - base;
+    if (lane == 0) RP[0] = 0;
+    // ---- my elements: value(s) + local row id, everything issued before anything is used
+    float x[KMAX], g[TWO ? KMAX : 1];
+    unsigned rpk[KMAX / 4];     // local row id + 1 of element k, one byte each (0 = no element)
+#pragma unroll
+    for (int k = 0; k < KMAX / 4; ++k) rpk[k] = 0u;
+#define ES_ROW(k) ((int)((rpk[(k) >> 2] >> (((k) & 3) * 8)) & 0xffu) - 1)
+    const float *pa = p.a + (int64_t)base * H, *pb = TWO ? p.b + (int64_t)base * H : nullptr;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int idx = k * 32 + lane;
+      x[k] = 0.f;
+      if (TWO) g[k] = 0.f;
+      if (idx < n) {
+        rpk[k >> 2] |= (unsigned)(__ldg(p.hub.edge_row + base + (idx >> lgH)) - rw + 1) << ((k & 3) * 8);
+        if (MODE != 2) x[k] = ld_stream(pa + idx);
+        if (TWO) g[k] = ld_stream(pb + idx);
+      }
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (ES_ROW(k) >= 0) {
+          const int c = __ldg(p.colind + base + ((k * 32 + lane) >> lgH));
+          const float z = __ldg(p.a + (int64_t)(rw + ES_ROW(k)) * H + h) + __ldg(p.b + (int64_t)c * H + h);
+          x[k] = z > 0.f ? z : z * p.slope;
+        }
+      }
+    }
+    __syncwarp();
+    // fold of the slot partials of one (row, head): slots touched by the row's edges, in slot order
+    auto merged = [&](int rl, int hh, bool is_max) {
+      const int k0 = RP[rl], deg = RP[rl + 1] - k0;
+      float acc = is_max ? -CUDART_INF_F : 0.f;
+      const int cnt = deg < S ? deg : S;
+      for (int j = 0; j < cnt; ++j) {
+        const int sl = deg < S ? ((k0 + j) & (S - 1)) : j;
+        const float v = SLA[(sl * 33 + rl) * H + hh];
+        acc = is_max ? fmaxf(acc, v) : acc + v;
+      }
+      return acc;
+    };
+    if (!TWO) {
+      // ---- pass 1: max
+      {
+        int cur = -1;
+        float mx = -CUDART_INF_F;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (ES_ROW(k) >= 0) {
+            if (ES_ROW(k) != cur) {
+              if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = mx;
+              cur = ES_ROW(k);
+              mx = x[k];
+            } else {
+              mx = fmaxf(mx, x[k]);
+            }
+          }
+        }
+        if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = mx;
+      }
+      __syncwarp();
+      for (int q = lane; q < m * H; q += 32) RS[q] = merged(q >> lgH, q & (H - 1), true);
+      __syncwarp();
+      // ---- pass 2: exp and sum
+      {
+        int cur = -1;
+        float sm = 0.f, mrow = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (ES_ROW(k) >= 0) {
+            if (ES_ROW(k) != cur) {
+              if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
+              cur = ES_ROW(k);
+              sm = 0.f;
+              mrow = RS[cur * H + h];
+            }
+            x[k] = es_exp(x[k] - mrow);
+            sm += x[k];
+          }
+        }
+        if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
+      }
+      __syncwarp();
+      for (int q = lane; q < m * H; q += 32) RS[q] = 1.f / merged(q >> lgH, q & (H - 1), false);
+      __syncwarp();
+      // ---- pass 3: normalise, store
+      float *o = p.out + (int64_t)base * H;
+      {
+        int cur = -1;
+        float inv = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (ES_ROW(k) >= 0) {
+            if (ES_ROW(k) != cur) { cur = ES_ROW(k); inv = RS[cur * H + h]; }
+            st_stream(o + k * 32 + lane, x[k] * inv);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      // ---- pass 1: sum y * g
+      {
+        int cur = -1;
+        float sm = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (ES_ROW(k) >= 0) {
+            if (ES_ROW(k) != cur) {
+              if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
+              cur = ES_ROW(k);
+              sm = 0.f;
+            }
+            sm = fmaf(x[k], g[k], sm);
+          }
+        }
+        if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
+      }
+      __syncwarp();
+      for (int q = lane; q < m * H; q += 32) RS[q] = merged(q >> lgH, q & (H - 1), false);
+      __syncwarp();
+      // ---- pass 2: y * (g - s) [* leakyrelu'], store; MODE 3 also folds the row sums of the result
+      float *o = p.out + (int64_t)base * H;
+      {
+        int cur = -1;
+        float srow = 0.f, hlrow = 0.f, sm = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (ES_ROW(k) >= 0) {
+            if (ES_ROW(k) != cur) {
+              if (MODE == 3 && cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
+              cur = ES_ROW(k);
+              srow = RS[cur * H + h];
+              if (MODE == 3) { hlrow = __ldg(p.hl + (int64_t)(rw + cur) * H + h); sm = 0.f; }
+            }
+            float v = x[k] * (g[k] - srow);
+            if (MODE == 3) {
+              const int c = __ldg(p.colind + base + ((k * 32 + lane) >> lgH));
+              const float z = hlrow + __ldg(p.hr + (int64_t)c * H + h);
+              v *= (z > 0.f ? 1.f : p.slope);
+              sm += v;
+            }
+            st_stream(o + k * 32 + lane, v);
+          }
+        }
+        if (MODE == 3 && cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
+      }
+      __syncwarp();
+      if (MODE == 3) {
+        for (int q = lane; q < m * H; q += 32) p.grow[(int64_t)rw * H + q] = merged(q >> lgH, q & (H - 1), false);  // empty rows: 0
+      }
+      __syncwarp();
+    }
+    rw += m;
+  }
+#undef ES_ROW
+}
+
 // ---------------------------------------------------------------- generic H: warp per row, loop over heads
 template <int MODE>
 __global__ void __launch_bounds__(256) es_generic_kernel(const EsParams p) {
@@ -572,10 +785,25 @@ static int es_launch(EsParams p, const cogdl_b200_hub_plan_t *plan, cudaStream_t
     es_stats_kernel<MODE><<<(unsigned)ceil_div((int64_t)p.hub.n_chunks * 32, 256), 256, 0, s>>>(p);
     CB_LAUNCH_CHECK();
   }
-  static int cap_floor = -1;
+  static int cap_floor = -1, use_reg = -1;
   if (cap_floor < 0) {
-    const char *e = getenv("COGDL_B200_ES_CAP");   // tuning only: smallest tile (floats per warp) to use
+    const char *e = getenv("COGDL_B200_ES_CAP");   // tuning only: smallest tile (floats per warp) of the staged kernel
     cap_floor = e ? atoi(e) : 0;
+    const char *r = getenv("COGDL_B200_ES_REG");   // tuning only: 0 disables the register-resident kernel
+    use_reg = r ? atoi(r) : 1;
+  }
+  if (use_reg && cap_need <= 1024) {
+    constexpr int RW = 4;
+    const int64_t items = (int64_t)p.hub.n_chunks + p.hub.n_segs;
+    const int64_t blocks = ceil_div(items, RW);
+    CB_REQUIRE(blocks <= 0x7fffffffLL, "%s: problem too large for one launch", who);
+    note_kernel("cogdl_b200::es_reg_kernel<MODE=%d,KMAX=%d,WARPS=4> (register-resident windows)", MODE, cap_need <= 512 ? 16 : 32);
+    if (blocks > 0) {
+      if (cap_need <= 512) es_reg_kernel<MODE, 16, RW><<<(unsigned)blocks, RW * 32, 0, s>>>(p);
+      else es_reg_kernel<MODE, 32, RW><<<(unsigned)blocks, RW * 32, 0, s>>>(p);
+      CB_LAUNCH_CHECK();
+    }
+    return COGDL_B200_OK;
   }
   const int64_t cap = cap_need > cap_floor ? cap_need : cap_floor;
   const int chosen = cap <= 512 ? 512 : (cap <= 1024 ? 1024 : 2048);
