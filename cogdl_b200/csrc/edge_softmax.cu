@@ -789,8 +789,9 @@ static int es_launch(EsParams p, const cogdl_b200_hub_plan_t *plan, cudaStream_t
   if (cap_floor < 0) {
     const char *e = getenv("COGDL_B200_ES_CAP");   // tuning only: smallest tile (floats per warp) of the staged kernel
     cap_floor = e ? atoi(e) : 0;
-    const char *r = getenv("COGDL_B200_ES_REG");   // tuning only: 0 disables the register-resident kernel
-    use_reg = r ? atoi(r) : 1;
+    const char *r = getenv("COGDL_B200_ES_REG");   // experiments: 1 selects the register-resident kernel (measured
+    use_reg = r ? atoi(r) : 0;                     // SLOWER on B200: 89 vs 64 us at arxiv H=8 -- fewer instructions, but
+                                                   // 24 warps/SM of 2 KB windows leave the per-window latency chain exposed)
   }
   if (use_reg && cap_need <= 1024) {
     constexpr int RW = 4;

@@ -9,8 +9,9 @@
 // This is the only tensor-core work on the hot path (north star: "tensor cores only where a dense
 // feature x weight GEMM is fused onto the aggregated output").
 //
-// One persistent CTA per SM, 16 warps, a tile = 128 consecutive destination rows:
-//   1. AGGREGATE (all warps): each warp streams the edges of its 8 rows exactly like the row-stream SpMM
+// One persistent CTA per SM, 32 warps, a tile = 128 consecutive destination rows:
+//   1. AGGREGATE (all warps): the tile's rows are dealt to the warps in contiguous runs of ~equal EDGE count
+//      (rowptr of the tile staged one tile ahead); each warp streams the edges of its rows like the row-stream SpMM
 //      (stream.cuh: 32-edge slabs, ballot row-end masks, U independent 512-byte gathers in flight, CSR order
 //      with separate fp32 mul / add => the aggregated tile is bit-identical to the SpMM output).  At a row end
 //      the fp32 row is NOT stored to global memory: it is split into three bf16 terms a = a1 + a2 + a3
@@ -23,7 +24,7 @@
 //      K = 16, W^T resident in shared memory (split the same way once per CTA).  Dropped terms are <= 2^-24
 //      relative: measured error vs an fp64 product ~1e-7 of the row scale, i.e. better than an fp32 FFMA GEMM
 //      (TF32 would give 1e-3, plain bf16 4e-3; tests/test_cpu_oracle_and_host.py emulates the split in numpy).
-//   3. EPILOGUE (all warps): tcgen05.ld the accumulator (lane = row, 32 columns per warp), add rowsum * bias,
+//   3. EPILOGUE (all warps): tcgen05.ld the accumulator (lane = row, 16 columns per warp), add rowsum * bias,
 //      ReLU, store.
 // No reference counterpart as a kernel; callers cogdl/layers/gcn_layer.py:51-64 (and sage_layer.py:69-87 for the
 // aggregate-then-linear order).  K (input width) must be 128, Fout <= 128.
@@ -41,9 +42,8 @@ namespace fg {
 
 constexpr int TILE_M = 128;
 constexpr int KDIM = 128;
-constexpr int WARPS = 16;
-constexpr int ROWS_PER_WARP = TILE_M / WARPS;        // 8
-constexpr int U = 8;                                  // gathers in flight per warp
+constexpr int WARPS = 32;
+constexpr int U = 4;                                  // gathers in flight per warp (32 warps x 4 x 512 B = 64 KB per SM)
 constexpr int SLAB_BYTES_A = TILE_M * 128;            // one K-slab (64 bf16 = 128 B per row) of A: 16 KB
 constexpr int A_BYTES = 3 * 2 * SLAB_BYTES_A;         // 3 splits x 2 K-slabs = 96 KB
 constexpr int W_MAX_BYTES = 3 * 2 * 128 * 128;        // 96 KB at Fout = 128
@@ -52,7 +52,8 @@ constexpr int OFF_ROWSUM = OFF_W + W_MAX_BYTES;
 constexpr int OFF_BIAS = OFF_ROWSUM + TILE_M * 4;
 constexpr int OFF_BAR = OFF_BIAS + 128 * 4;
 constexpr int OFF_TMEM = OFF_BAR + 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 8 + 1024;       // + slack to align the base to 1024 B (SWIZZLE_128B atoms)
+constexpr int OFF_TILE_RP = OFF_TMEM + 8;             // rowptr of the tile's 128 rows (+1), staged one tile ahead
+constexpr int SMEM_BYTES = OFF_TILE_RP + (TILE_M + 4) * 4 + 1024;       // + slack to align the base to 1024 B (SWIZZLE_128B atoms)
 
 struct Params {
   const int *rowptr;
@@ -116,6 +117,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
@@ -172,6 +184,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
   float *bias_s = reinterpret_cast<float *>(smem + OFF_BIAS);
   const uint32_t bar = smem_u32(smem + OFF_BAR);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
+  int *tile_rp = reinterpret_cast<int *>(smem + OFF_TILE_RP);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int w_slab_bytes = p.Npad * 128;
 
@@ -200,6 +213,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
     *reinterpret_cast<uint2 *>(smemW + 2 * 2 * w_slab_bytes + off) = make_uint2(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]));
   }
   if (tid < 128) bias_s[tid] = (p.bias && tid < p.Fout) ? __ldg(p.bias + tid) : 0.f;
+  if (tid <= TILE_M) tile_rp[tid] = __ldg(p.rowptr + min((int)blockIdx.x * TILE_M + tid, p.n_rows));
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -212,14 +226,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int row0 = tile * TILE_M;
-    // =========================================================== 1. aggregate my 8 rows into shared memory
+    // =========================================================== 1. aggregate my rows into shared memory
+    // rows are dealt to the 32 warps by EDGE count (contiguous runs with ~1/32 of the tile's edges each): on
+    // power-law rows an equal-rows split leaves most warps idle while one finishes (binary search in tile_rp)
     {
-      const int r_begin = row0 + warp * ROWS_PER_WARP;
-      const int r_end = min(r_begin + ROWS_PER_WARP, p.n_rows);
-      // rowptr of my rows: lane i < 9 holds rowptr[r_begin + i]
-      int rp = 0;
-      if (lane <= ROWS_PER_WARP && r_begin + lane <= p.n_rows) rp = __ldg(p.rowptr + r_begin + lane);
-      int next_row = r_begin;      // rows < next_row of my range have been written (or are handled)
+      const int rows_here = min(TILE_M, p.n_rows - row0);
+      const int e0 = tile_rp[0], e_tot = tile_rp[rows_here] - e0;
+      auto split = [&](int w) {          // first row whose start offset (edges + rows, so empty rows spread too) >= share w
+        if (w <= 0) return 0;
+        if (w >= WARPS) return rows_here;
+        const long long target = ((long long)(e_tot + rows_here) * w) / WARPS;
+        int lo = 0, hi = rows_here;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((long long)(tile_rp[mid] - e0) + mid < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const int r_begin = row0 + split(warp), r_end = row0 + split(warp + 1);
+      int next_row = r_begin;      // rows < next_row of my range have been written
       auto zero_rows = [&](int upto) {   // rows [next_row, upto): no edges -> zeros
         for (; next_row < upto; ++next_row) {
           store_row(smemA, next_row - row0, lane, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -228,14 +253,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
       };
       int r = r_begin;
       while (r < r_end) {
-        const int lb = __shfl_sync(FULL, rp, r - r_begin), hb = __shfl_sync(FULL, rp, r - r_begin + 1);
+        const int lb = tile_rp[r - row0], hb = tile_rp[r - row0 + 1];
         if (p.chunk_edges > 0 && hb - lb > p.chunk_edges) {
           // hub row: aggregated beforehand (hub chunks of the row-stream kernel); weight sum by a strided loop
-          zero_rows(r);
           const float4 a = __ldg(H4 + (int64_t)r * (KDIM / 4) + lane);
           float s = 0.f;
           if (p.val) {
-            for (int e = lb + lane; e < hb; e += 32) s += ld_stream(p.val + e);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int e = lb + lane;
+            for (; e + 96 < hb; e += 128) {
+              s0 += ld_stream(p.val + e); s1 += ld_stream(p.val + e + 32);
+              s2 += ld_stream(p.val + e + 64); s3 += ld_stream(p.val + e + 96);
+            }
+            for (; e < hb; e += 32) s0 += ld_stream(p.val + e);
+            s = (s0 + s1) + (s2 + s3);
             for (int st = 16; st > 0; st >>= 1) s += __shfl_xor_sync(FULL, s, st);
           } else {
             s = (float)(hb - lb);
@@ -248,12 +279,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         }
         // maximal run of non-hub rows [r, rb)
         int rb = r + 1;
-        while (rb < r_end) {
-          const int d = __shfl_sync(FULL, rp, rb - r_begin + 1) - __shfl_sync(FULL, rp, rb - r_begin);
-          if (p.chunk_edges > 0 && d > p.chunk_edges) break;
-          ++rb;
-        }
-        const int e_begin = lb, e_end = __shfl_sync(FULL, rp, rb - r_begin);
+        while (rb < r_end && !(p.chunk_edges > 0 && tile_rp[rb - row0 + 1] - tile_rp[rb - row0] > p.chunk_edges)) ++rb;
+        const int e_begin = lb, e_end = tile_rp[rb - row0];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float rs = 0.f;
         for (int e = e_begin; e < e_end; e += 32) {
@@ -298,10 +325,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         zero_rows(rb);     // trailing empty rows of the run
         r = rb;
       }
-      // rows of this warp beyond n_rows (last tile): zeros
-      for (int rr = max(next_row, r_end); rr < row0 + (warp + 1) * ROWS_PER_WARP; ++rr) {
-        store_row(smemA, rr - row0, lane, make_float4(0.f, 0.f, 0.f, 0.f));
-        if (lane == 0) rowsum_s[rr - row0] = 0.f;
+      // rows of the tile beyond n_rows (last tile): zeros, dealt round-robin
+      for (int rr = rows_here + warp; rr < TILE_M; rr += WARPS) {
+        store_row(smemA, rr, lane, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (lane == 0) rowsum_s[rr] = 0.f;
       }
     }
     fence_async_smem();          // generic-proxy writes of the tile -> visible to the tensor core (async proxy)
@@ -332,11 +359,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
     phase ^= 1u;
     tc_fence_after();
     {
+      constexpr int CW = 128 / (WARPS / 4);    // accumulator columns per warp: 16
       const int q = warp & 3;                  // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
-      const int c0 = (warp >> 2) * 32;         // its 32 accumulator columns
+      const int c0 = (warp >> 2) * CW;
       if (c0 < p.Npad) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        uint32_t v[CW];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         const int r = q * 32 + lane;
         const int grow = row0 + r;
         if (grow < p.n_rows) {
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
           float *o = p.out + (int64_t)grow * p.Fout + c0;
           const bool vec = (p.Fout % 4 == 0);
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          for (int c = 0; c < CW; c += 4) {
             float4 y;
             y.x = __uint_as_float(v[c + 0]) + rsum * bias_s[c0 + c + 0];
             y.y = __uint_as_float(v[c + 1]) + rsum * bias_s[c0 + c + 1];
@@ -362,6 +390,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
           }
         }
       }
+    }
+    // rowptr of the NEXT tile of this CTA (read again only after the barrier below)
+    {
+      const int nrow0 = (tile + (int)gridDim.x) * TILE_M;
+      if (tid <= TILE_M && nrow0 < p.n_rows) tile_rp[tid] = __ldg(p.rowptr + min(nrow0 + tid, p.n_rows));
     }
     tc_fence_before();
     __syncthreads();             // accumulator and operand tiles are free for the next tile

@@ -239,12 +239,20 @@ static int dispatch_spmm(const SpmmParams &p, cudaStream_t s) {
   // peer form: only the row-stream kernel decodes (owner << shift | row) columns (SRC_PEERS); the
   // sub-warp row kernel below would read them as X1[c - n0].  NV = 1 masks lanes >= fv.
   if (p.n_peers > 0 && fv <= 32) return launch_spmm_stream<VecT, 1>(p, s);
+  const bool stream = p.hub.n_segs > 0;
+  // narrow rows (F = 40 -> 10 float4): the lean row-stream form with the idle lanes masked beats the sub-warp
+  // row kernel once a row needs more than `stream_min_fv` vectors (measured, profiles/; tunable for experiments)
+  static int stream_min_fv = -1;
+  if (stream_min_fv < 0) {
+    const char *e = getenv("COGDL_B200_SPMM_STREAM_MINFV");
+    stream_min_fv = e ? atoi(e) : 9;
+  }
+  if (stream && fv >= stream_min_fv && fv <= 16) return launch_spmm_stream<VecT, 1>(p, s);
   if (fv <= 1) return launch_spmm<VecT, 1, 1>(p, s);
   if (fv <= 2) return launch_spmm<VecT, 2, 1>(p, s);
   if (fv <= 4) return launch_spmm<VecT, 4, 1>(p, s);
   if (fv <= 8) return launch_spmm<VecT, 8, 1>(p, s);
   if (fv <= 16) return launch_spmm<VecT, 16, 1>(p, s);
-  const bool stream = p.hub.n_segs > 0;
   if (fv <= 32) return stream ? launch_spmm_stream<VecT, 1>(p, s) : launch_spmm<VecT, 32, 1>(p, s);
   if (sizeof(VecT) == 4 && fv > 64) return stream ? launch_spmm_stream<VecT, 4>(p, s) : launch_spmm<VecT, 32, 4>(p, s);
   return stream ? launch_spmm_stream<VecT, 2>(p, s) : launch_spmm<VecT, 32, 2>(p, s);

@@ -140,6 +140,86 @@ __device__ __forceinline__ void stream_range(const StreamParams &p, int e, const
   }
 }
 
+// Lean form of stream_range for the plain SpMM (NV == 1, weighted / unweighted, any source form).  The
+// round-1 loop spent ~47 warp-instructions per edge (ncu: issue-bound at 62 % issue-active on the L2-resident
+// arxiv shape): three SHFL broadcasts per edge, each guarded by a BRA.DIV convergence check, and two
+// predicate branches with BSSY/BSYNC pairs around every gather and every accumulate.  Here the slab
+// (column, value, row) is parked in shared memory once (3 STS per 32 edges) and read back with broadcast LDS
+// (no convergence requirement, column + value in ONE LDS.64), full batches run without per-edge predicates, and
+// the row-end test is made once per batch on the ballot mask: ~15 instructions per edge.  Same accumulation
+// order and rounding as stream_range (CSR order, separate fp32 multiply and add) => still bit-identical to
+// the reference CPU loop on unsplit rows.
+template <typename VecT, int MODE, int SRC, int U, bool ROWS>
+__device__ __forceinline__ void stream_range_lean(const StreamParams &p, int e, const int e_end, const int cv, const bool colok,
+                                                  const int lane, int2 *s_cv, int *s_r, VecT &acc) {
+  const VecT *X0 = reinterpret_cast<const VecT *>(p.X0) + cv;
+  const VecT *X1 = reinterpret_cast<const VecT *>(p.X1) + cv;
+  VecT *Y = reinterpret_cast<VecT *>(p.Y) + cv;
+  auto src_ptr = [&](int cj) -> const VecT * {
+    if (SRC == SRC_ONE || cj < p.n0) return X0 + (int64_t)cj * p.ldv;
+    if (SRC == SRC_TWO) return X1 + ((int64_t)cj - p.n0) * p.ldv;
+    const unsigned r = (unsigned)(cj - (int)p.n0);      // remote row: read it from the owner's HBM over NVLink
+    return reinterpret_cast<const VecT *>(p.peers[r >> p.peer_shift]) + cv + (int64_t)(r & ((1u << p.peer_shift) - 1u)) * p.ldv;
+  };
+  auto accumulate = [&](float vj, const VecT &x) {
+    if (MODE == MODE_UNWEIGHTED) sk_add(acc, x); else axpy_rn(acc, vj, x);
+  };
+  for (; e < e_end; e += 32) {
+    const int cnt = min(32, e_end - e);
+    const int q = e + lane;
+    int c = 0, rid = -1, rnx = -1;
+    float v = 0.f;
+    if (q < e_end) {
+      c = ld_stream(p.colind + q);
+      if (MODE == MODE_WEIGHTED) v = ld_stream(p.val + q);
+      if (ROWS) {
+        rid = ld_stream(p.hub.edge_row + q);
+        if (q + 1 < e_end) rnx = __ldg(p.hub.edge_row + q + 1);
+      }
+    }
+    const unsigned endmask = ROWS ? __ballot_sync(FULL, lane < cnt && rid != rnx) : 0u;
+    __syncwarp();                                   // everybody is done reading the previous slab
+    s_cv[lane] = make_int2(c, __float_as_int(v));
+    if (ROWS) s_r[lane] = rid;
+    __syncwarp();
+    int j = 0;
+#pragma unroll 1
+    for (; j + U <= cnt; j += U) {                  // full batches: no per-edge predicates
+      int2 cw[U];
+      VecT x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) cw[u] = s_cv[j + u];            // broadcast LDS.64
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (colok) x[u] = ld_gather(src_ptr(cw[u].x));
+      const unsigned em = ROWS ? ((endmask >> j) & ((1u << U) - 1u)) : 0u;
+      if (em == 0u) {                               // no row ends inside this batch
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (colok) accumulate(__int_as_float(cw[u].y), x[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (colok) accumulate(__int_as_float(cw[u].y), x[u]);
+          if ((em >> u) & 1u) {                     // last edge of its row: store and restart (warp-uniform)
+            const int rj = s_r[j + u];
+            if (colok) { st_stream(Y + (int64_t)rj * p.ldv, acc); acc = sk_zero<VecT>(); }
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (; j < cnt; ++j) {                          // tail of the last slab: one edge at a time
+      const int2 cw = s_cv[j];
+      if (colok) accumulate(__int_as_float(cw.y), ld_gather(src_ptr(cw.x)));
+      if (ROWS && ((endmask >> j) & 1u)) {
+        const int rj = s_r[j];
+        if (colok) { st_stream(Y + (int64_t)rj * p.ldv, acc); acc = sk_zero<VecT>(); }
+      }
+    }
+  }
+}
+
 template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, int MINB, bool PREFETCH, bool HINT>
 __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p) {
   constexpr int TILE = 32 * NV;
@@ -149,6 +229,11 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
   const int slice = (MODE == MODE_MULTIHEAD) ? (int)(wid - item * p.S) : 0;
   VecT *Y = reinterpret_cast<VecT *>(p.Y);
   VecT *P = reinterpret_cast<VecT *>(p.hub.partials);
+  constexpr bool LEAN = (NV == 1 && MODE != MODE_MULTIHEAD && !HINT);
+  __shared__ int2 s_cv_all[LEAN ? 8 : 1][32];
+  __shared__ int s_r_all[LEAN ? 8 : 1][32];
+  int2 *s_cv = s_cv_all[LEAN ? (threadIdx.x >> 5) : 0];
+  int *s_r = s_r_all[LEAN ? (threadIdx.x >> 5) : 0];
 
   // column tiles: the multi-head form owns exactly one 32-vector slice; the plain form loops over
   // the row in TILE-vector passes (one pass for F <= 128 * NV)
@@ -164,7 +249,8 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
 #pragma unroll
       for (int k = 0; k < NV; ++k) { colok[k] = (cv + k * 32) < p.ldv; acc[k] = sk_zero<VecT>(); }
       const int head = (MODE == MODE_MULTIHEAD && colok[0]) ? cv / p.FVL : 0;
-      stream_range<VecT, NV, MODE, HAS_PERM, SRC, U, false, PREFETCH, HINT>(p, w.lb, w.hb, cv, colok, head, lane, acc);
+      if constexpr (LEAN) stream_range_lean<VecT, MODE, SRC, U, false>(p, w.lb, w.hb, cv, colok[0], lane, s_cv, s_r, acc[0]);
+      else stream_range<VecT, NV, MODE, HAS_PERM, SRC, U, false, PREFETCH, HINT>(p, w.lb, w.hb, cv, colok, head, lane, acc);
 #pragma unroll
       for (int k = 0; k < NV; ++k)
         if (colok[k]) st_cg(P + (int64_t)w.slot * p.ldv + cv + k * 32, acc[k]);
@@ -208,7 +294,8 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
         }
       }
     }
-    stream_range<VecT, NV, MODE, HAS_PERM, SRC, U, true, PREFETCH, HINT>(p, e_begin, e_end, cv, colok, head, lane, acc);
+    if constexpr (LEAN) stream_range_lean<VecT, MODE, SRC, U, true>(p, e_begin, e_end, cv, colok[0], lane, s_cv, s_r, acc[0]);
+    else stream_range<VecT, NV, MODE, HAS_PERM, SRC, U, true, PREFETCH, HINT>(p, e_begin, e_end, cv, colok, head, lane, acc);
   }
 }
 
