@@ -177,6 +177,9 @@ __global__ void __launch_bounds__(256) es_warp_kernel(const EsParams p) {
 // The last chunk of the row to arrive merges the chunks' values in chunk order into stats[first].
 template <int MODE>
 __global__ void __launch_bounds__(256) es_stats_kernel(const EsParams p) {
+  // programmatic dependent launch: the main kernel may start as soon as every CTA of this grid is running; its
+  // segment items need nothing from us, its chunk items wait (griddepcontrol.wait) for this grid to finish
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int64_t item = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (item >= p.hub.n_chunks) return;
@@ -252,7 +255,7 @@ __device__ __forceinline__ void es_chunk_item(const EsParams &p, int64_t item, i
     const WorkItem w = decode_item(item, 0, p.rowptr, p.hub);
     const int head = lane & (H - 1);
     const int n = (w.hb - w.lb) * H;
-    const float2 rs = __ldg(p.stats + (int64_t)w.first * H + head);
+    const float2 rs = __ldcg(p.stats + (int64_t)w.first * H + head);
     float *o = p.out + (int64_t)w.lb * H;
     if (TWO) {
       const float *y = p.a + (int64_t)w.lb * H, *g = p.b + (int64_t)w.lb * H;
@@ -330,15 +333,18 @@ __global__ void __launch_bounds__(WARPS * 32) es_main_kernel(const EsParams p) {
   const int64_t item = (int64_t)blockIdx.x * WARPS + wib;
   const int H = p.H;
 
-  // ------------------------------------------------ hub chunk: normalise with the row's merged statistics
-  if (item < p.hub.n_chunks) {
-    es_chunk_item<MODE>(p, item, lane);
+  // ------------------------------------------------ hub chunk (LAST in the grid): normalise with the row's merged
+  // statistics, which the statistics kernel -- possibly still running: programmatic dependent launch -- produces
+  if (item >= p.hub.n_segs) {
+    if (item - p.hub.n_segs < p.hub.n_chunks) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      es_chunk_item<MODE>(p, item - p.hub.n_segs, lane);
+    }
     return;
   }
 
   // ------------------------------------------------ segment of short rows
-  const int64_t seg = item - p.hub.n_chunks;
-  if (seg >= p.hub.n_segs) return;
+  const int64_t seg = item;
   const int2 rr = __ldg(p.hub.segs + seg);
   float *T = tiles + (size_t)wib * CAP * (TWO ? 2 : 1);
   float *T2 = T + CAP;
@@ -743,8 +749,18 @@ static int launch_main(const EsParams &p, cudaStream_t s) {
   const int64_t blocks = ceil_div(items, WARPS);
   if (blocks == 0) return COGDL_B200_OK;
   CB_REQUIRE(blocks <= 0x7fffffffLL, "edge_softmax: problem too large for one launch");
-  es_main_kernel<MODE, CAP, WARPS><<<(unsigned)blocks, WARPS * 32, smem, s>>>(p);
-  CB_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;     // overlap with the statistics kernel (see es_stats_kernel)
+  cfg.attrs = attr;
+  cfg.numAttrs = p.hub.n_chunks > 0 ? 1 : 0;
+  CB_CUDA(cudaLaunchKernelEx(&cfg, es_main_kernel<MODE, CAP, WARPS>, p));
+  count_launch();
   return COGDL_B200_OK;
 }
 
