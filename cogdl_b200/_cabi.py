@@ -72,7 +72,7 @@ SIGNATURES = {
     "cogdl_b200_scatter_max_bwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "cogdl_b200_gat_fwd_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _i64, _i64, _plan_p, _vp]),
     "cogdl_b200_gcn_fused_supported": (ctypes.c_int, [_i64, _i64]),
-    "cogdl_b200_gcn_fused_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _plan_p, _vp]),
+    "cogdl_b200_gcn_fused_f32": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _plan_p, _vp]),
     "cogdl_b200_coo2csr_workspace_bytes": (_i64, [_i64, _i64]),
     "cogdl_b200_coo2csr_index": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "cogdl_b200_narrow_i64_i32": (ctypes.c_int, [_vp, _vp, _i64, _vp]),

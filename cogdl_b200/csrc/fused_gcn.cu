@@ -64,6 +64,7 @@ struct Params {
   const float *W;          // [Fout, 128]  (nn.Linear weight layout = K-major B operand)
   const float *bias;       // nullable [Fout]
   const float *hub_agg;    // [n_rows, 128]: rows with degree > chunk_edges hold (A.X)[row]
+  const float *rowsum;     // nullable [n_rows]: (A.1)[row], cached by the caller for fixed edge weights
   float *out;              // [n_rows, Fout]
   int n_rows;
   int Fout;
@@ -258,15 +259,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
           // hub row: aggregated beforehand (hub chunks of the row-stream kernel); weight sum by a strided loop
           const float4 a = __ldg(H4 + (int64_t)r * (KDIM / 4) + lane);
           float s = 0.f;
-          if (p.val) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          if (p.rowsum) {
+            s = __ldg(p.rowsum + r);
+          } else if (p.val) {      // no cached row sums: one warp sums the hub's weights, 8 loads in flight per lane
+            float sa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             int e = lb + lane;
-            for (; e + 96 < hb; e += 128) {
-              s0 += ld_stream(p.val + e); s1 += ld_stream(p.val + e + 32);
-              s2 += ld_stream(p.val + e + 64); s3 += ld_stream(p.val + e + 96);
+            for (; e + 7 * 32 < hb; e += 256) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) sa[t] += ld_stream(p.val + e + 32 * t);
             }
-            for (; e < hb; e += 32) s0 += ld_stream(p.val + e);
-            s = (s0 + s1) + (s2 + s3);
+            for (; e < hb; e += 32) sa[0] += ld_stream(p.val + e);
+            s = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
             for (int st = 16; st > 0; st >>= 1) s += __shfl_xor_sync(FULL, s, st);
           } else {
             s = (float)(hb - lb);
@@ -411,7 +414,8 @@ using namespace cogdl_b200;
 extern "C" int cogdl_b200_gcn_fused_supported(int64_t K, int64_t Fout) { return (K == fg::KDIM && Fout >= 1 && Fout <= 128) ? 1 : 0; }
 
 extern "C" int cogdl_b200_gcn_fused_f32(const int32_t *rowptr, const int32_t *colind, const float *val, const float *X,
-                                        const float *W, const float *bias, float *out, float *hub_agg, int64_t n_rows,
+                                        const float *W, const float *bias, const float *rowsum, float *out, float *hub_agg,
+                                        int64_t n_rows,
                                         int64_t K, int64_t Fout, int32_t relu, const cogdl_b200_hub_plan_t *plan,
                                         cogdl_b200_stream_t stream) {
   const char *who = "cogdl_b200_gcn_fused_f32";
@@ -433,7 +437,7 @@ extern "C" int cogdl_b200_gcn_fused_f32(const int32_t *rowptr, const int32_t *co
   }
   fg::Params p;
   p.rowptr = rowptr; p.colind = colind; p.val = val; p.edge_row = plan->edge_row; p.X = X; p.W = W; p.bias = bias;
-  p.hub_agg = hub_agg ? hub_agg : X; p.out = out; p.n_rows = (int)n_rows; p.Fout = (int)Fout;
+  p.hub_agg = hub_agg ? hub_agg : X; p.rowsum = rowsum; p.out = out; p.n_rows = (int)n_rows; p.Fout = (int)Fout;
   p.Npad = (int)((Fout + 15) / 16 * 16); p.chunk_edges = plan->chunk_edges; p.relu = relu;
   p.n_tiles = (int)ceil_div(n_rows, fg::TILE_M);
   static int n_sms = 0;

@@ -287,11 +287,13 @@ COGDL_B200_API int cogdl_b200_edge_colsum_f32(const int32_t *colptr, const int32
  * scale.  X [n_src,K], W [Fout,K] (torch.nn.Linear.weight layout), bias [Fout] or NULL, out [n_rows,Fout].
  * Needs K == 128, Fout <= 128 (cogdl_b200_gcn_fused_supported), a hub plan with edge_row, 16-byte aligned
  * X / W / out.  hub_agg: scratch [n_rows, K] fp32, required iff the plan has hub rows (only those rows are
- * written); plan->partials as for cogdl_b200_spmm_csr_f32 (n_chunks*K*4 bytes).
+ * written); plan->partials as for cogdl_b200_spmm_csr_f32 (n_chunks*K*4 bytes).  rowsum: optional [n_rows]
+ * = A.1 (sum of each row's edge values), worth caching when the edge weights are fixed (GCN); NULL =>
+ * the kernel sums the weights itself (one warp per hub row: slow on 10^4-edge hubs).
  * ------------------------------------------------------------------------------------- */
 COGDL_B200_API int cogdl_b200_gcn_fused_supported(int64_t K, int64_t Fout);
 COGDL_B200_API int cogdl_b200_gcn_fused_f32(const int32_t *rowptr, const int32_t *colind, const float *val, const float *X,
-                             const float *W, const float *bias, float *out, float *hub_agg, int64_t n_rows,
+                             const float *W, const float *bias, const float *rowsum, float *out, float *hub_agg, int64_t n_rows,
                              int64_t K, int64_t Fout, int32_t relu, const cogdl_b200_hub_plan_t *plan,
                              cogdl_b200_stream_t stream);
 

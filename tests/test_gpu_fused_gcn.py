@@ -90,6 +90,8 @@ def test_fused_layer_matches_reference_order_fp64(dev, name, fout, weighted):
         for relu in (False, True):
             out = fused_gcn_raw(st, val, x, W, b, relu)
             assert err(out, ref_layer(rp, ci, val, x, W, b, relu)) <= TOL, (chunk, relu)
+            out = fused_gcn_raw(st, val, x, W, b, relu, cache_rowsum=False)      # hub weight sums inside the kernel
+            assert err(out, ref_layer(rp, ci, val, x, W, b, relu)) <= TOL, (chunk, relu, "no cached row sums")
         # W = I, no bias: the fused kernel's aggregated tile is the SpMM output (re-assembled from its three bf16 terms)
         if fout == 128:
             out = fused_gcn_raw(st, val, x, torch.eye(128, device=dev), None, False)
