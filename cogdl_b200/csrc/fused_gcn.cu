@@ -53,7 +53,9 @@ constexpr int OFF_BIAS = OFF_ROWSUM + TILE_M * 4;
 constexpr int OFF_BAR = OFF_BIAS + 128 * 4;
 constexpr int OFF_TMEM = OFF_BAR + 8;
 constexpr int OFF_TILE_RP = OFF_TMEM + 8;             // rowptr of the tile's 128 rows (+1), staged one tile ahead
-constexpr int SMEM_BYTES = OFF_TILE_RP + (TILE_M + 4) * 4 + 1024;       // + slack to align the base to 1024 B (SWIZZLE_128B atoms)
+constexpr int OFF_TILE_COST = OFF_TILE_RP + (TILE_M + 4) * 4;   // prefix of the rows' COST (hub rows count as 4 edges)
+constexpr int OFF_SLAB = OFF_TILE_COST + (TILE_M + 4) * 4;      // per warp: 32 x (column, value) + 32 x row
+constexpr int SMEM_BYTES = OFF_SLAB + WARPS * 32 * 12 + 1024;       // + slack to align the base to 1024 B (SWIZZLE_128B atoms)
 
 struct Params {
   const int *rowptr;
@@ -175,6 +177,35 @@ __device__ __forceinline__ void store_row(unsigned char *smemA, int r, int lane,
   *reinterpret_cast<uint2 *>(smemA + 2 * 2 * SLAB_BYTES_A + off) = make_uint2(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]));
 }
 
+// rowptr and cost prefix of one tile -> shared memory (one warp: lane L takes rows 4L .. 4L+3).  cost(row) =
+// 1 + min(deg, hub ? 4 : deg): hub rows are one 512-byte read here, their edges were consumed by the hub pre-pass
+__device__ __forceinline__ void stage_tile(const Params &p, int row0, int lane, int *tile_rp, int *tile_cost) {
+  int rp[5];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) rp[t] = __ldg(p.rowptr + min(row0 + 4 * lane + t, p.n_rows));
+  int c[4], tot = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int d = rp[t + 1] - rp[t];
+    c[t] = (row0 + 4 * lane + t < p.n_rows) ? 1 + ((p.chunk_edges > 0 && d > p.chunk_edges) ? 4 : d) : 0;
+    tot += c[t];
+  }
+  int incl = tot;
+#pragma unroll
+  for (int st = 1; st < 32; st <<= 1) {
+    const int o = __shfl_up_sync(FULL, incl, st);
+    if (lane >= st) incl += o;
+  }
+  int run = incl - tot;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    tile_rp[4 * lane + t] = rp[t];
+    tile_cost[4 * lane + t] = run;
+    run += c[t];
+  }
+  if (lane == 31) { tile_rp[TILE_M] = rp[4]; tile_cost[TILE_M] = run; }
+}
+
 __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p) {
   extern __shared__ unsigned char fg_smem_raw[];
   // SWIZZLE_128B atoms need a 1024-byte aligned base
@@ -186,6 +217,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
   const uint32_t bar = smem_u32(smem + OFF_BAR);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
   int *tile_rp = reinterpret_cast<int *>(smem + OFF_TILE_RP);
+  int *tile_cost = reinterpret_cast<int *>(smem + OFF_TILE_COST);
+  int2 *s_cv = reinterpret_cast<int2 *>(smem + OFF_SLAB) + (threadIdx.x >> 5) * 32;
+  int *s_r = reinterpret_cast<int *>(smem + OFF_SLAB + WARPS * 32 * 8) + (threadIdx.x >> 5) * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int w_slab_bytes = p.Npad * 128;
 
@@ -214,7 +248,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
     *reinterpret_cast<uint2 *>(smemW + 2 * 2 * w_slab_bytes + off) = make_uint2(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]));
   }
   if (tid < 128) bias_s[tid] = (p.bias && tid < p.Fout) ? __ldg(p.bias + tid) : 0.f;
-  if (tid <= TILE_M) tile_rp[tid] = __ldg(p.rowptr + min((int)blockIdx.x * TILE_M + tid, p.n_rows));
+  if (warp == 1) stage_tile(p, (int)blockIdx.x * TILE_M, lane, tile_rp, tile_cost);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -232,15 +266,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
     // power-law rows an equal-rows split leaves most warps idle while one finishes (binary search in tile_rp)
     {
       const int rows_here = min(TILE_M, p.n_rows - row0);
-      const int e0 = tile_rp[0], e_tot = tile_rp[rows_here] - e0;
-      auto split = [&](int w) {          // first row whose start offset (edges + rows, so empty rows spread too) >= share w
+      const int c_tot = tile_cost[rows_here];
+      auto split = [&](int w) {          // first row whose cost prefix >= share w
         if (w <= 0) return 0;
         if (w >= WARPS) return rows_here;
-        const long long target = ((long long)(e_tot + rows_here) * w) / WARPS;
+        const int target = (int)(((long long)c_tot * w) / WARPS);
         int lo = 0, hi = rows_here;
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
-          if ((long long)(tile_rp[mid] - e0) + mid < target) lo = mid + 1; else hi = mid;
+          if (tile_cost[mid] < target) lo = mid + 1; else hi = mid;
         }
         return lo;
       };
@@ -298,31 +332,44 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
             if (q + 1 < e_end) rnx = __ldg(p.edge_row + q + 1);
           }
           const unsigned endmask = __ballot_sync(FULL, lane < cnt && rid != rnx);
+          __syncwarp();                                  // previous slab fully consumed
+          s_cv[lane] = make_int2(c, __float_as_int(v));  // slab parked in shared memory: broadcast LDS.64 instead of
+          s_r[lane] = rid;                               // three shuffles + convergence checks per edge (stream.cuh)
+          __syncwarp();
+          auto flush = [&](int rj) {                     // last edge of row rj
+            zero_rows(rj);
+            store_row(smemA, rj - row0, lane, acc);
+            if (lane == 0) rowsum_s[rj - row0] = rs;
+            next_row = rj + 1;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            rs = 0.f;
+          };
+          int j = 0;
 #pragma unroll 1
-          for (int j = 0; j < cnt; j += U) {
+          for (; j + U <= cnt; j += U) {
+            int2 cw[U];
             float4 x[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int cj = __shfl_sync(FULL, c, (j + u) & 31);
-              if (j + u < cnt) x[u] = ld_gather(X4 + (int64_t)cj * (KDIM / 4) + lane);
-            }
+            for (int u = 0; u < U; ++u) cw[u] = s_cv[j + u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = ld_gather(X4 + (int64_t)cw[u].x * (KDIM / 4) + lane);
+            const unsigned em = (endmask >> j) & ((1u << U) - 1u);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const float vj = __shfl_sync(FULL, v, (j + u) & 31);
-              const int rj = __shfl_sync(FULL, rid, (j + u) & 31);
-              if (j + u < cnt) {
-                if (p.val) axpy_rn(acc, vj, x[u]); else add_rn(acc, x[u]);
-                rs += vj;
-                if ((endmask >> (j + u)) & 1u) {        // last edge of row rj (warp-uniform)
-                  zero_rows(rj);
-                  store_row(smemA, rj - row0, lane, acc);
-                  if (lane == 0) rowsum_s[rj - row0] = rs;
-                  next_row = rj + 1;
-                  acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                  rs = 0.f;
-                }
-              }
+              const float vj = __int_as_float(cw[u].y);
+              if (p.val) axpy_rn(acc, vj, x[u]); else add_rn(acc, x[u]);
+              rs += vj;
+              if (em != 0u && ((em >> u) & 1u)) flush(s_r[j + u]);
             }
+          }
+#pragma unroll 1
+          for (; j < cnt; ++j) {
+            const int2 cw = s_cv[j];
+            const float4 x = ld_gather(X4 + (int64_t)cw.x * (KDIM / 4) + lane);
+            const float vj = __int_as_float(cw.y);
+            if (p.val) axpy_rn(acc, vj, x); else add_rn(acc, x);
+            rs += vj;
+            if ((endmask >> j) & 1u) flush(s_r[j]);
           }
         }
         zero_rows(rb);     // trailing empty rows of the run
@@ -394,11 +441,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         }
       }
     }
-    // rowptr of the NEXT tile of this CTA (read again only after the barrier below)
-    {
-      const int nrow0 = (tile + (int)gridDim.x) * TILE_M;
-      if (tid <= TILE_M && nrow0 < p.n_rows) tile_rp[tid] = __ldg(p.rowptr + min(nrow0 + tid, p.n_rows));
-    }
+    // rowptr + cost prefix of the NEXT tile of this CTA (read again only after the barrier below)
+    if (warp == 1 && tile + (int)gridDim.x < p.n_tiles) stage_tile(p, (tile + (int)gridDim.x) * TILE_M, lane, tile_rp, tile_cost);
     tc_fence_before();
     __syncthreads();             // accumulator and operand tiles are free for the next tile
     tc_fence_after();
