@@ -42,8 +42,9 @@ namespace fg {
 
 constexpr int TILE_M = 128;
 constexpr int KDIM = 128;
-constexpr int WARPS = 32;
-constexpr int U = 4;                                  // gathers in flight per warp (32 warps x 4 x 512 B = 64 KB per SM)
+constexpr int WARPS = 16;
+constexpr int U = 8;                                  // gathers per batch; two batches in flight per warp (software pipelined):
+                                                      // 16 warps x 16 x 512 B = 128 KB of feature rows in flight per SM
 constexpr int SLAB_BYTES_A = TILE_M * 128;            // one K-slab (64 bf16 = 128 B per row) of A: 16 KB
 constexpr int A_BYTES = 3 * 2 * SLAB_BYTES_A;         // 3 splits x 2 K-slabs = 96 KB
 constexpr int W_MAX_BYTES = 3 * 2 * 128 * 128;        // 96 KB at Fout = 128
@@ -131,6 +132,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
@@ -209,7 +213,7 @@ __device__ __forceinline__ void stage_tile(const Params &p, int row0, int lane, 
 __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p) {
   extern __shared__ unsigned char fg_smem_raw[];
   // SWIZZLE_128B atoms need a 1024-byte aligned base
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fg_smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *smem = fg_smem_raw + ((1024u - (smem_u32(fg_smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   unsigned char *smemA = smem;
   unsigned char *smemW = smem + OFF_W;
   float *rowsum_s = reinterpret_cast<float *>(smem + OFF_ROWSUM);
@@ -320,57 +324,66 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         const int e_begin = lb, e_end = tile_rp[rb - row0];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float rs = 0.f;
+        auto flush = [&](int rj) {                       // last edge of row rj
+          zero_rows(rj);
+          store_row(smemA, rj - row0, lane, acc);
+          if (lane == 0) rowsum_s[rj - row0] = rs;
+          next_row = rj + 1;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          rs = 0.f;
+        };
+        // slab registers (column, value, row, row of the next edge); the NEXT slab is fetched while this one is used
+        int c = 0, rid = -1, rnx = -1;
+        float v = 0.f;
+        auto load_slab = [&](int e0, int &c_, float &v_, int &rid_, int &rnx_) {
+          const int q = e0 + lane;
+          c_ = 0; v_ = 0.f; rid_ = -1; rnx_ = -1;
+          if (q < e_end) {
+            c_ = ld_stream(p.colind + q);
+            v_ = p.val ? ld_stream(p.val + q) : 1.f;
+            rid_ = ld_stream(p.edge_row + q);
+            if (q + 1 < e_end) rnx_ = __ldg(p.edge_row + q + 1);
+          }
+        };
+        load_slab(e_begin, c, v, rid, rnx);
         for (int e = e_begin; e < e_end; e += 32) {
           const int cnt = min(32, e_end - e);
-          const int q = e + lane;
-          int c = 0, rid = -1, rnx = -1;
-          float v = 0.f;
-          if (q < e_end) {
-            c = ld_stream(p.colind + q);
-            v = p.val ? ld_stream(p.val + q) : 1.f;
-            rid = ld_stream(p.edge_row + q);
-            if (q + 1 < e_end) rnx = __ldg(p.edge_row + q + 1);
-          }
           const unsigned endmask = __ballot_sync(FULL, lane < cnt && rid != rnx);
           __syncwarp();                                  // previous slab fully consumed
           s_cv[lane] = make_int2(c, __float_as_int(v));  // slab parked in shared memory: broadcast LDS.64 instead of
           s_r[lane] = rid;                               // three shuffles + convergence checks per edge (stream.cuh)
           __syncwarp();
-          auto flush = [&](int rj) {                     // last edge of row rj
-            zero_rows(rj);
-            store_row(smemA, rj - row0, lane, acc);
-            if (lane == 0) rowsum_s[rj - row0] = rs;
-            next_row = rj + 1;
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            rs = 0.f;
+          int cn, ridn, rnxn;
+          float vn;
+          load_slab(e + 32, cn, vn, ridn, rnxn);
+          // two batches of U gathers in flight: batch b+1 is issued before batch b is consumed
+          float4 xa[U], xb[U];
+          auto load_batch = [&](float4 (&x)[U], int j) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (j + u < cnt) x[u] = ld_gather(X4 + (int64_t)s_cv[j + u].x * (KDIM / 4) + lane);
           };
-          int j = 0;
-#pragma unroll 1
-          for (; j + U <= cnt; j += U) {
-            int2 cw[U];
-            float4 x[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) cw[u] = s_cv[j + u];
-#pragma unroll
-            for (int u = 0; u < U; ++u) x[u] = ld_gather(X4 + (int64_t)cw[u].x * (KDIM / 4) + lane);
+          auto consume = [&](const float4 (&x)[U], int j) {
             const unsigned em = (endmask >> j) & ((1u << U) - 1u);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              const float vj = __int_as_float(cw[u].y);
-              if (p.val) axpy_rn(acc, vj, x[u]); else add_rn(acc, x[u]);
-              rs += vj;
-              if (em != 0u && ((em >> u) & 1u)) flush(s_r[j + u]);
+              if (j + u < cnt) {
+                const float vj = __int_as_float(s_cv[j + u].y);
+                if (p.val) axpy_rn(acc, vj, x[u]); else add_rn(acc, x[u]);
+                rs += vj;
+                if (em != 0u && ((em >> u) & 1u)) flush(s_r[j + u]);
+              }
             }
-          }
+          };
+          load_batch(xa, 0);
 #pragma unroll 1
-          for (; j < cnt; ++j) {
-            const int2 cw = s_cv[j];
-            const float4 x = ld_gather(X4 + (int64_t)cw.x * (KDIM / 4) + lane);
-            const float vj = __int_as_float(cw.y);
-            if (p.val) axpy_rn(acc, vj, x); else add_rn(acc, x);
-            rs += vj;
-            if ((endmask >> j) & 1u) flush(s_r[j]);
+          for (int j = 0; j < cnt; j += 2 * U) {
+            if (j + U < cnt) load_batch(xb, j + U);
+            consume(xa, j);
+            if (j + 2 * U < cnt) load_batch(xa, j + 2 * U);
+            if (j + U < cnt) consume(xb, j + U);
           }
+          c = cn; v = vn; rid = ridn; rnx = rnxn;
         }
         zero_rows(rb);     // trailing empty rows of the run
         r = rb;
@@ -409,12 +422,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
     phase ^= 1u;
     tc_fence_after();
     {
-      constexpr int CW = 128 / (WARPS / 4);    // accumulator columns per warp: 16
+      constexpr int CW = 128 / (WARPS / 4);    // accumulator columns per warp: 32
       const int q = warp & 3;                  // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
       const int c0 = (warp >> 2) * CW;
       if (c0 < p.Npad) {
         uint32_t v[CW];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         const int r = q * 32 + lane;
         const int grow = row0 + r;
         if (grow < p.n_rows) {
