@@ -9,8 +9,11 @@
 // This is the only tensor-core work on the hot path (north star: "tensor cores only where a dense
 // feature x weight GEMM is fused onto the aggregated output").
 //
-// One persistent CTA per SM, 32 warps, a tile = 128 consecutive destination rows:
-//   1. AGGREGATE (all warps): the tile's rows are dealt to the warps in contiguous runs of ~equal EDGE count
+// One persistent CTA per SM made of TWO independent 8-warp groups; each group owns a tile of 64 consecutive
+// destination rows (its own operand buffer, TMEM accumulator, mbarrier and named barrier) and both share W^T.
+// The groups drift apart by construction, so while one waits for its tensor-core products and writes its output
+// the other keeps the SM's load pipeline busy (a single 128-row tile per SM left it idle ~40 % of the time: ncu).
+//   1. AGGREGATE (the group's warps): the tile's rows are dealt to the warps in contiguous runs of ~equal COST
 //      (rowptr of the tile staged one tile ahead); each warp streams the edges of its rows like the row-stream SpMM
 //      (stream.cuh: 32-edge slabs, ballot row-end masks, U independent 512-byte gathers in flight, CSR order
 //      with separate fp32 mul / add => the aggregated tile is bit-identical to the SpMM output).  At a row end
@@ -19,12 +22,12 @@
 //      in the tcgen05 K-major SWIZZLE_128B operand layout.  Hub rows (degree > plan chunk) were aggregated
 //      beforehand by the hub-chunk items of the row-stream kernel (deterministic in-order combine) and are
 //      picked up from a scratch matrix.
-//   2. MMA (one thread): D[128 x Fout] (fp32, TMEM) = sum over the six split products a_i . w_j with i + j <= 4
+//   2. MMA (one thread): D[64 x Fout] (fp32, TMEM) = sum over the six split products a_i . w_j with i + j <= 4
 //      (a3.w1, a2.w2, a1.w3, a2.w1, a1.w2, a1.w1 -- small terms first), each 8 x tcgen05.mma.kind::f16 of
 //      K = 16, W^T resident in shared memory (split the same way once per CTA).  Dropped terms are <= 2^-24
 //      relative: measured error vs an fp64 product ~1e-7 of the row scale, i.e. better than an fp32 FFMA GEMM
 //      (TF32 would give 1e-3, plain bf16 4e-3; tests/test_cpu_oracle_and_host.py emulates the split in numpy).
-//   3. EPILOGUE (all warps): tcgen05.ld the accumulator (lane = row, 16 columns per warp), add rowsum * bias,
+//   3. EPILOGUE (the group's warps): tcgen05.ld the accumulator (data path = row), add rowsum * bias,
 //      ReLU, store.
 // No reference counterpart as a kernel; callers cogdl/layers/gcn_layer.py:51-64 (and sage_layer.py:69-87 for the
 // aggregate-then-linear order).  K (input width) must be 128, Fout <= 128.
@@ -40,23 +43,23 @@ int spmm_hub_rows_only(const int32_t *rowptr, const int32_t *colind, const float
 
 namespace fg {
 
-constexpr int TILE_M = 128;
+constexpr int TILE_M = 64;                            // rows per tile (UMMA M = 64); two tiles are in flight per CTA
+constexpr int GROUPS = 2;                             // independent warp groups, one tile each, W^T shared
+constexpr int GWARPS = 8;                             // warps per group
+constexpr int WARPS = GROUPS * GWARPS;
 constexpr int KDIM = 128;
-constexpr int WARPS = 16;
 constexpr int U = 8;                                  // gathers per batch; two batches in flight per warp (software pipelined):
                                                       // 16 warps x 16 x 512 B = 128 KB of feature rows in flight per SM
-constexpr int SLAB_BYTES_A = TILE_M * 128;            // one K-slab (64 bf16 = 128 B per row) of A: 16 KB
-constexpr int A_BYTES = 3 * 2 * SLAB_BYTES_A;         // 3 splits x 2 K-slabs = 96 KB
+constexpr int SLAB_BYTES_A = TILE_M * 128;            // one K-slab (64 bf16 = 128 B per row) of a tile: 8 KB
+constexpr int A_TILE_BYTES = 3 * 2 * SLAB_BYTES_A;    // 3 splits x 2 K-slabs = 48 KB per group
 constexpr int W_MAX_BYTES = 3 * 2 * 128 * 128;        // 96 KB at Fout = 128
-constexpr int OFF_W = A_BYTES;
-constexpr int OFF_ROWSUM = OFF_W + W_MAX_BYTES;
-constexpr int OFF_BIAS = OFF_ROWSUM + TILE_M * 4;
-constexpr int OFF_BAR = OFF_BIAS + 128 * 4;
-constexpr int OFF_TMEM = OFF_BAR + 8;
-constexpr int OFF_TILE_RP = OFF_TMEM + 8;             // rowptr of the tile's 128 rows (+1), staged one tile ahead
-constexpr int OFF_TILE_COST = OFF_TILE_RP + (TILE_M + 4) * 4;   // prefix of the rows' COST (hub rows count as 4 edges)
-constexpr int OFF_SLAB = OFF_TILE_COST + (TILE_M + 4) * 4;      // per warp: 32 x (column, value) + 32 x row
-constexpr int SMEM_BYTES = OFF_SLAB + WARPS * 32 * 12 + 1024;       // + slack to align the base to 1024 B (SWIZZLE_128B atoms)
+constexpr int OFF_W = GROUPS * A_TILE_BYTES;
+constexpr int OFF_BIAS = OFF_W + W_MAX_BYTES;
+constexpr int OFF_TMEM = OFF_BIAS + 128 * 4;
+constexpr int OFF_GROUP = OFF_TMEM + 16;              // per group: rowsum[64] | tile_rp[68] | tile_cost[68] | mbarrier
+constexpr int GROUP_BYTES = TILE_M * 4 + 2 * (TILE_M + 4) * 4 + 16;
+constexpr int OFF_SLAB = OFF_GROUP + GROUPS * GROUP_BYTES;      // per warp: 32 x (column, value) + 32 x row
+constexpr int SMEM_BYTES = OFF_SLAB + WARPS * 32 * 12 + 1024;   // + slack to align the base to 1024 B (SWIZZLE_128B atoms)
 
 struct Params {
   const int *rowptr;
@@ -82,6 +85,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) {     // named barrier of one warp group (ids 1, 2; 0 is __syncthreads)
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GWARPS * 32) : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -121,20 +127,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
-
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
@@ -168,30 +160,30 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
   return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
 }
 
-// write one aggregated row (lane owns columns 4*lane .. 4*lane+3) into the three split operands
-__device__ __forceinline__ void store_row(unsigned char *smemA, int r, int lane, const float4 &acc) {
+// write one aggregated row (lane owns columns 4*lane .. 4*lane+3) into the three split operands of a tile
+__device__ __forceinline__ void store_row(unsigned char *tileA, int r, int lane, const float4 &acc) {
   __nv_bfloat16 s1[4], s2[4], s3[4];
   split3(acc.x, s1[0], s2[0], s3[0]);
   split3(acc.y, s1[1], s2[1], s3[1]);
   split3(acc.z, s1[2], s2[2], s3[2]);
   split3(acc.w, s1[3], s2[3], s3[3]);
   const uint32_t off = sw128_offset(r, 4 * lane, SLAB_BYTES_A);
-  *reinterpret_cast<uint2 *>(smemA + 0 * 2 * SLAB_BYTES_A + off) = make_uint2(pack2(s1[0], s1[1]), pack2(s1[2], s1[3]));
-  *reinterpret_cast<uint2 *>(smemA + 1 * 2 * SLAB_BYTES_A + off) = make_uint2(pack2(s2[0], s2[1]), pack2(s2[2], s2[3]));
-  *reinterpret_cast<uint2 *>(smemA + 2 * 2 * SLAB_BYTES_A + off) = make_uint2(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]));
+  *reinterpret_cast<uint2 *>(tileA + 0 * 2 * SLAB_BYTES_A + off) = make_uint2(pack2(s1[0], s1[1]), pack2(s1[2], s1[3]));
+  *reinterpret_cast<uint2 *>(tileA + 1 * 2 * SLAB_BYTES_A + off) = make_uint2(pack2(s2[0], s2[1]), pack2(s2[2], s2[3]));
+  *reinterpret_cast<uint2 *>(tileA + 2 * 2 * SLAB_BYTES_A + off) = make_uint2(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]));
 }
 
-// rowptr and cost prefix of one tile -> shared memory (one warp: lane L takes rows 4L .. 4L+3).  cost(row) =
-// 1 + min(deg, hub ? 4 : deg): hub rows are one 512-byte read here, their edges were consumed by the hub pre-pass
+// rowptr and cost prefix of one 64-row tile -> shared memory (one warp: lane L takes rows 2L, 2L+1).  cost(row) =
+// 1 + (hub ? 4 : deg): hub rows are one 512-byte read here, their edges were consumed by the hub pre-pass
 __device__ __forceinline__ void stage_tile(const Params &p, int row0, int lane, int *tile_rp, int *tile_cost) {
-  int rp[5];
+  int rp[3];
 #pragma unroll
-  for (int t = 0; t < 5; ++t) rp[t] = __ldg(p.rowptr + min(row0 + 4 * lane + t, p.n_rows));
-  int c[4], tot = 0;
+  for (int t = 0; t < 3; ++t) rp[t] = __ldg(p.rowptr + min(row0 + 2 * lane + t, p.n_rows));
+  int c[2], tot = 0;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < 2; ++t) {
     const int d = rp[t + 1] - rp[t];
-    c[t] = (row0 + 4 * lane + t < p.n_rows) ? 1 + ((p.chunk_edges > 0 && d > p.chunk_edges) ? 4 : d) : 0;
+    c[t] = (row0 + 2 * lane + t < p.n_rows) ? 1 + ((p.chunk_edges > 0 && d > p.chunk_edges) ? 4 : d) : 0;
     tot += c[t];
   }
   int incl = tot;
@@ -202,38 +194,43 @@ __device__ __forceinline__ void stage_tile(const Params &p, int row0, int lane, 
   }
   int run = incl - tot;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    tile_rp[4 * lane + t] = rp[t];
-    tile_cost[4 * lane + t] = run;
+  for (int t = 0; t < 2; ++t) {
+    tile_rp[2 * lane + t] = rp[t];
+    tile_cost[2 * lane + t] = run;
     run += c[t];
   }
-  if (lane == 31) { tile_rp[TILE_M] = rp[4]; tile_cost[TILE_M] = run; }
+  if (lane == 31) { tile_rp[TILE_M] = rp[2]; tile_cost[TILE_M] = run; }
 }
 
 __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p) {
   extern __shared__ unsigned char fg_smem_raw[];
   // SWIZZLE_128B atoms need a 1024-byte aligned base
   unsigned char *smem = fg_smem_raw + ((1024u - (smem_u32(fg_smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
-  unsigned char *smemA = smem;
-  unsigned char *smemW = smem + OFF_W;
-  float *rowsum_s = reinterpret_cast<float *>(smem + OFF_ROWSUM);
-  float *bias_s = reinterpret_cast<float *>(smem + OFF_BIAS);
-  const uint32_t bar = smem_u32(smem + OFF_BAR);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
-  int *tile_rp = reinterpret_cast<int *>(smem + OFF_TILE_RP);
-  int *tile_cost = reinterpret_cast<int *>(smem + OFF_TILE_COST);
-  int2 *s_cv = reinterpret_cast<int2 *>(smem + OFF_SLAB) + (threadIdx.x >> 5) * 32;
-  int *s_r = reinterpret_cast<int *>(smem + OFF_SLAB + WARPS * 32 * 8) + (threadIdx.x >> 5) * 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = warp / GWARPS, gw = warp % GWARPS, gtid = tid - g * GWARPS * 32;   // my group, warp / thread inside it
+  unsigned char *tileA = smem + g * A_TILE_BYTES;
+  unsigned char *smemW = smem + OFF_W;
+  float *bias_s = reinterpret_cast<float *>(smem + OFF_BIAS);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
+  unsigned char *gbase = smem + OFF_GROUP + g * GROUP_BYTES;
+  float *rowsum_s = reinterpret_cast<float *>(gbase);
+  int *tile_rp = reinterpret_cast<int *>(gbase + TILE_M * 4);
+  int *tile_cost = tile_rp + (TILE_M + 4);
+  const uint32_t bar = smem_u32(gbase + TILE_M * 4 + 2 * (TILE_M + 4) * 4);
+  int2 *s_cv = reinterpret_cast<int2 *>(smem + OFF_SLAB) + warp * 32;
+  int *s_r = reinterpret_cast<int *>(smem + OFF_SLAB + WARPS * 32 * 8) + warp * 32;
   const int w_slab_bytes = p.Npad * 128;
+  const int tile_stride = (int)gridDim.x * GROUPS;
+  const int first_tile = (int)blockIdx.x * GROUPS + g;
 
-  // ---- one-time setup: TMEM, barrier, W^T split into three bf16 operands (SW128 K-major), bias
+  // ---- one-time setup: TMEM (one 128-column accumulator per group), barriers, W^T split into three bf16
+  //      operands (SW128 K-major), bias
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid == 32) {
+  if (gtid == 32) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -252,29 +249,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
     *reinterpret_cast<uint2 *>(smemW + 2 * 2 * w_slab_bytes + off) = make_uint2(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]));
   }
   if (tid < 128) bias_s[tid] = (p.bias && tid < p.Fout) ? __ldg(p.bias + tid) : 0.f;
-  if (warp == 1) stage_tile(p, (int)blockIdx.x * TILE_M, lane, tile_rp, tile_cost);
+  if (gw == 1 && first_tile < p.n_tiles) stage_tile(p, first_tile * TILE_M, lane, tile_rp, tile_cost);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // M = 64 accumulators occupy data paths {0-15, 32-47, 64-79, 96-111} (cute tmem_frg, UMMA_1SM M_MMA = 64);
+  // group 1 takes the next 128 columns
+  const uint32_t tmem_acc = *tmem_slot + (uint32_t)(g * 128);
   const uint32_t idesc = make_idesc(p.Npad);
   const float4 *X4 = reinterpret_cast<const float4 *>(p.X);
   const float4 *H4 = reinterpret_cast<const float4 *>(p.hub_agg);
   uint32_t phase = 0;
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  // ===== the two groups run this loop independently (named barriers): while one is in its MMA / epilogue, the other
+  //       keeps the SM's memory pipeline busy with its gather
+  for (int tile = first_tile; tile < p.n_tiles; tile += tile_stride) {
     const int row0 = tile * TILE_M;
     // =========================================================== 1. aggregate my rows into shared memory
-    // rows are dealt to the 32 warps by EDGE count (contiguous runs with ~1/32 of the tile's edges each): on
-    // power-law rows an equal-rows split leaves most warps idle while one finishes (binary search in tile_rp)
+    // rows are dealt to the group's 8 warps by COST (contiguous runs; hub rows count as 4 edges): on power-law
+    // rows an equal-rows split leaves most warps idle while one finishes (binary search in the cost prefix)
     {
       const int rows_here = min(TILE_M, p.n_rows - row0);
       const int c_tot = tile_cost[rows_here];
       auto split = [&](int w) {          // first row whose cost prefix >= share w
         if (w <= 0) return 0;
-        if (w >= WARPS) return rows_here;
-        const int target = (int)(((long long)c_tot * w) / WARPS);
+        if (w >= GWARPS) return rows_here;
+        const int target = (int)(((long long)c_tot * w) / GWARPS);
         int lo = 0, hi = rows_here;
         while (lo < hi) {
           const int mid = (lo + hi) >> 1;
@@ -282,11 +283,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         }
         return lo;
       };
-      const int r_begin = row0 + split(warp), r_end = row0 + split(warp + 1);
+      const int r_begin = row0 + split(gw), r_end = row0 + split(gw + 1);
       int next_row = r_begin;      // rows < next_row of my range have been written
       auto zero_rows = [&](int upto) {   // rows [next_row, upto): no edges -> zeros
         for (; next_row < upto; ++next_row) {
-          store_row(smemA, next_row - row0, lane, make_float4(0.f, 0.f, 0.f, 0.f));
+          store_row(tileA, next_row - row0, lane, make_float4(0.f, 0.f, 0.f, 0.f));
           if (lane == 0) rowsum_s[next_row - row0] = 0.f;
         }
       };
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
       while (r < r_end) {
         const int lb = tile_rp[r - row0], hb = tile_rp[r - row0 + 1];
         if (p.chunk_edges > 0 && hb - lb > p.chunk_edges) {
-          // hub row: aggregated beforehand (hub chunks of the row-stream kernel); weight sum by a strided loop
+          // hub row: aggregated beforehand (hub chunks of the row-stream kernel)
           const float4 a = __ldg(H4 + (int64_t)r * (KDIM / 4) + lane);
           float s = 0.f;
           if (p.rowsum) {
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
           } else {
             s = (float)(hb - lb);
           }
-          store_row(smemA, r - row0, lane, a);
+          store_row(tileA, r - row0, lane, a);
           if (lane == 0) rowsum_s[r - row0] = s;
           next_row = r + 1;
           ++r;
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         float rs = 0.f;
         auto flush = [&](int rj) {                       // last edge of row rj
           zero_rows(rj);
-          store_row(smemA, rj - row0, lane, acc);
+          store_row(tileA, rj - row0, lane, acc);
           if (lane == 0) rowsum_s[rj - row0] = rs;
           next_row = rj + 1;
           acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -389,18 +390,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         r = rb;
       }
       // rows of the tile beyond n_rows (last tile): zeros, dealt round-robin
-      for (int rr = rows_here + warp; rr < TILE_M; rr += WARPS) {
-        store_row(smemA, rr, lane, make_float4(0.f, 0.f, 0.f, 0.f));
+      for (int rr = rows_here + gw; rr < TILE_M; rr += GWARPS) {
+        store_row(tileA, rr, lane, make_float4(0.f, 0.f, 0.f, 0.f));
         if (lane == 0) rowsum_s[rr] = 0.f;
       }
     }
     fence_async_smem();          // generic-proxy writes of the tile -> visible to the tensor core (async proxy)
     tc_fence_before();
-    __syncthreads();
+    group_sync(g);
     // =========================================================== 2. six split products into TMEM (one thread)
-    if (tid == 0) {
+    if (gtid == 0) {
       tc_fence_after();
-      const uint32_t a_base = smem_u32(smemA), w_base = smem_u32(smemW);
+      const uint32_t a_base = smem_u32(tileA), w_base = smem_u32(smemW);
       // (i, j): split of A x split of W, smallest terms first
       const int ai[6] = {2, 1, 0, 1, 0, 0};
       const int wj[6] = {0, 1, 2, 0, 1, 0};
@@ -411,56 +412,63 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
         for (int ks = 0; ks < KDIM / 16; ++ks) {            // K = 16 bf16 = 32 bytes per instruction
           const uint32_t ka = a_base + ai[t] * 2 * SLAB_BYTES_A + (ks >> 2) * SLAB_BYTES_A + (ks & 3) * 32;
           const uint32_t kb = w_base + wj[t] * 2 * w_slab_bytes + (ks >> 2) * w_slab_bytes + (ks & 3) * 32;
-          umma_bf16(tmem_base, make_desc(ka), make_desc(kb), idesc, accumulate);
+          umma_bf16(tmem_acc, make_desc(ka), make_desc(kb), idesc, accumulate);
           accumulate = 1;
         }
       }
       umma_commit(bar);
     }
+    // rowptr + cost prefix of my NEXT tile while the tensor core works (read again only after the barrier below)
+    if (gw == 1 && tile + tile_stride < p.n_tiles) stage_tile(p, (tile + tile_stride) * TILE_M, lane, tile_rp, tile_cost);
     // =========================================================== 3. epilogue: TMEM -> registers -> global
     mbar_wait(bar, phase);
     phase ^= 1u;
     tc_fence_after();
     {
-      constexpr int CW = 128 / (WARPS / 4);    // accumulator columns per warp: 32
-      const int q = warp & 3;                  // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
-      const int c0 = (warp >> 2) * CW;
-      if (c0 < p.Npad) {
-        uint32_t v[CW];
-        tmem_ld(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        const int r = q * 32 + lane;
-        const int grow = row0 + r;
-        if (grow < p.n_rows) {
-          const float rsum = rowsum_s[r];
-          float *o = p.out + (int64_t)grow * p.Fout + c0;
-          const bool vec = (p.Fout % 4 == 0);
+      // warp gw may read TMEM data paths [32 q, 32 q + 32), q = gw % 4; an M = 64 accumulator keeps rows
+      // 16 q .. 16 q + 15 in the FIRST 16 of them (lanes 16..31 of the warp idle here); the group's two warps with the
+      // same q split the 128 columns: four 32-column loads cover 64 columns each
+      const int q = gw & 3;
+      const int r = q * 16 + (lane & 15);
+      const int grow = row0 + r;
+      const bool live = (lane < 16) && grow < p.n_rows;
+      const float rsum = rowsum_s[r];
+      const bool vec = (p.Fout % 4 == 0);
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = (gw >> 2) * 64 + cc * 32;
+        if (c0 < p.Npad) {                       // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          if (live) {
+            float *o = p.out + (int64_t)grow * p.Fout + c0;
 #pragma unroll
-          for (int c = 0; c < CW; c += 4) {
-            float4 y;
-            y.x = __uint_as_float(v[c + 0]) + rsum * bias_s[c0 + c + 0];
-            y.y = __uint_as_float(v[c + 1]) + rsum * bias_s[c0 + c + 1];
-            y.z = __uint_as_float(v[c + 2]) + rsum * bias_s[c0 + c + 2];
-            y.w = __uint_as_float(v[c + 3]) + rsum * bias_s[c0 + c + 3];
-            if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-            if (vec && c0 + c + 3 < p.Fout) {
-              __stcs(reinterpret_cast<float4 *>(o + c), y);
-            } else {
-              if (c0 + c + 0 < p.Fout) o[c + 0] = y.x;
-              if (c0 + c + 1 < p.Fout) o[c + 1] = y.y;
-              if (c0 + c + 2 < p.Fout) o[c + 2] = y.z;
-              if (c0 + c + 3 < p.Fout) o[c + 3] = y.w;
+            for (int c = 0; c < 32; c += 4) {
+              float4 y;
+              y.x = __uint_as_float(v[c + 0]) + rsum * bias_s[c0 + c + 0];
+              y.y = __uint_as_float(v[c + 1]) + rsum * bias_s[c0 + c + 1];
+              y.z = __uint_as_float(v[c + 2]) + rsum * bias_s[c0 + c + 2];
+              y.w = __uint_as_float(v[c + 3]) + rsum * bias_s[c0 + c + 3];
+              if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+              if (vec && c0 + c + 3 < p.Fout) {
+                __stcs(reinterpret_cast<float4 *>(o + c), y);
+              } else {
+                if (c0 + c + 0 < p.Fout) o[c + 0] = y.x;
+                if (c0 + c + 1 < p.Fout) o[c + 1] = y.y;
+                if (c0 + c + 2 < p.Fout) o[c + 2] = y.z;
+                if (c0 + c + 3 < p.Fout) o[c + 3] = y.w;
+              }
             }
           }
         }
       }
     }
-    // rowptr + cost prefix of the NEXT tile of this CTA (read again only after the barrier below)
-    if (warp == 1 && tile + (int)gridDim.x < p.n_tiles) stage_tile(p, (tile + (int)gridDim.x) * TILE_M, lane, tile_rp, tile_cost);
     tc_fence_before();
-    __syncthreads();             // accumulator and operand tiles are free for the next tile
+    group_sync(g);               // accumulator, operand tile and staged rowptr are free / ready for the next tile
     tc_fence_after();
   }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(256) : "memory");
 }
 
 }  // namespace fg
@@ -506,8 +514,9 @@ extern "C" int cogdl_b200_gcn_fused_f32(const int32_t *rowptr, const int32_t *co
     CB_CUDA(cudaFuncSetAttribute(fg::gcn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fg::SMEM_BYTES));
     attr_done = true;
   }
-  const int grid = p.n_tiles < n_sms ? p.n_tiles : n_sms;
-  note_kernel("cogdl_b200::fg::gcn_fused_kernel<tile 128x%d, K=128, bf16x3 split, tcgen05.mma kind::f16>", p.Npad);
+  const int want = (p.n_tiles + fg::GROUPS - 1) / fg::GROUPS;
+  const int grid = want < n_sms ? want : n_sms;
+  note_kernel("cogdl_b200::fg::gcn_fused_kernel<2 groups x tile 64x%d, K=128, bf16x3 split, tcgen05.mma kind::f16>", p.Npad);
   fg::gcn_fused_kernel<<<grid, fg::WARPS * 32, fg::SMEM_BYTES, s>>>(p);
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;
