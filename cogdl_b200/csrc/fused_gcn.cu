@@ -127,6 +127,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Feature-row gathers bypass the L1: this kernel leaves the SM ~16 KB of L1 (212 KB of shared memory), and an L1-allocating
+// load holds a line per 128 bytes in flight -- 128 lines cap the SM at ~32 row gathers in flight, whatever the warp count
+// or unroll depth (measured: three different schedules all landed on the same time).  ld.global.cg is tracked outside the
+// L1 data array.
+__device__ __forceinline__ float4 fg_gather(const float4 *p) { return __ldcg(p); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
@@ -362,7 +368,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gcn_fused_kernel(const Params p
           auto load_batch = [&](float4 (&x)[U], int j) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
-              if (j + u < cnt) x[u] = ld_gather(X4 + (int64_t)s_cv[j + u].x * (KDIM / 4) + lane);
+              if (j + u < cnt) x[u] = fg_gather(X4 + (int64_t)s_cv[j + u].x * (KDIM / 4) + lane);
           };
           auto consume = [&](const float4 (&x)[U], int j) {
             const unsigned em = (endmask >> j) & ((1u << U) - 1u);
