@@ -261,7 +261,15 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
       for (int cv = lane; cv < p.ldv; cv += 32) {
         const VecT *pp = P + (int64_t)w.first * p.ldv + cv;
         VecT s = ld_cg(pp);
-        for (int q = 1; q < w.n_row_chunks; ++q) sk_add(s, ld_cg(pp + (int64_t)q * p.ldv));
+        int q = 1;
+        for (; q + 8 <= w.n_row_chunks; q += 8) {      // 8 partials in flight, added in chunk order (a 22 K-edge
+          VecT t[8];                                   // hub has 354 of them: this loop is the kernel's tail)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = ld_cg(pp + (int64_t)(q + u) * p.ldv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) sk_add(s, t[u]);
+        }
+        for (; q < w.n_row_chunks; ++q) sk_add(s, ld_cg(pp + (int64_t)q * p.ldv));
         st_stream(Y + (int64_t)w.row * p.ldv + cv, s);
       }
     }
