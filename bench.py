@@ -574,12 +574,58 @@ def extras(torch, flush, synth, steps=10):
         backward_and_piece_extras(torch, flush, bench, res, g, st, n, nnz, dev)
     except Exception as ex:  # noqa: BLE001
         res["backward_extras_error"] = f"{type(ex).__name__}: {ex}"
-    try:   # fused (A.X).W + bias + ReLU with tcgen05 vs spmm + cuBLAS + elementwise
-        from cogdl_b200.operators.fused_gcn import bench_fused_vs_unfused
+    try:   # fused (A.X).W^T + (A.1) b^T + ReLU with tcgen05 vs SpMM + cuBLAS, one 128 -> 128 GCN layer
+        from cogdl_b200.operators.fused_gcn import fused_gcn_raw
 
-        res.update(bench_fused_vs_unfused(torch, st, w, x128, lambda name, fn: bench(name, fn, nnz * (4 * 128 + 8) + n * (4 * 128 + 4), nnz)))
+        lin = torch.nn.Linear(128, 128).to(dev)
+        W, b = lin.weight.detach().contiguous(), lin.bias.detach().contiguous()
+        layer_bytes = nnz * (4 * 128 + 8) + n * (4 * 128 + 4)
+        tf32_was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False      # the 1e-5 bar rules TF32 out for the unfused comparison
+        bench("C2_gcn_layer_fused_tcgen05", lambda: fused_gcn_raw(st, w, x128, W, b, True), layer_bytes, nnz)
+        bench("C2_gcn_layer_unfused_fp32_reference_order", lambda: torch.relu_(spmm_raw(st, w, torch.addmm(b, x128, W.t()))),
+              layer_bytes, nnz)
+        bench("C2_gcn_layer_unfused_fp32_spmm_then_gemm", lambda: torch.relu_(spmm_raw(st, w, x128) @ W.t()), layer_bytes, nnz)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        bench("C2_gcn_layer_unfused_tf32_reference_order", lambda: torch.relu_(spmm_raw(st, w, torch.addmm(b, x128, W.t()))),
+              layer_bytes, nnz)
+        torch.backends.cuda.matmul.allow_tf32 = tf32_was
+        a = fused_gcn_raw(st, w, x128, W, b, True).double()
+        r = torch.relu(torch.sparse_csr_tensor(st.rowptr.long(), st.colind.long(), w.double(), size=(st.n_rows, st.n_cols))
+                       @ (x128.double() @ W.double().t() + b.double()))
+        scale = torch.maximum(r.abs(), r.abs().amax(dim=1, keepdim=True)).clamp_min(1e-30)
+        res["C2_gcn_layer_fused_tcgen05"]["max_rel_err_vs_fp64_reference_order"] = float(((a - r).abs() / scale).max())
+        res["C2_gcn_layer_fused_tcgen05"]["kernel"] = cogdl_b200._cabi.last_kernel()
+        del a, r, scale, lin
     except Exception as ex:  # noqa: BLE001
         res["fused_gcn_error"] = f"{type(ex).__name__}: {ex}"
+    try:   # device neighbour sampler vs the reference's host loop (sample.cpp compiled unmodified), SURVEY 8f-4
+        import oracle
+        from cogdl_b200 import sampling
+
+        rp64, col64 = g.row_indptr.contiguous(), g.col_indices.contiguous()
+        batch = torch.randperm(n, generator=torch.Generator().manual_seed(0))[:4096].to(dev)
+        for size, tag in ((10, "k10"), (-1, "full")):
+            fn = lambda: sampling.sample_adj(rp64, col64, batch, size, False, seed=1)
+            ms = time_steps(fn, steps, 3, None, torch, False)
+            t = statistics.median(ms) / 1e3
+            out = fn()
+            ent = {"ms": t * 1e3, "sampled_edges": int(out[3].numel()), "sampled_edges_per_s": int(out[3].numel()) / t,
+                   "what": f"sample_adj: 4096 seed nodes, {'all' if size < 0 else size} neighbours, arxiv shape"}
+            if oracle.ref_available("sampler", "o3"):
+                smp = oracle.ref_module("sampler", "o3")
+                a3 = (rp64.cpu(), col64.cpu(), batch.cpu())
+                smp.sample_adj(*a3, size, False)
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    smp.sample_adj(*a3, size, False)
+                    ts.append(time.perf_counter() - t0)
+                ent["reference_cpu_ms"] = statistics.median(ts) * 1e3
+                ent["speedup_vs_reference_cpu"] = ent["reference_cpu_ms"] / ent["ms"]
+            res["C4op_sample_adj_" + tag] = ent
+    except Exception as ex:  # noqa: BLE001
+        res["sampler_error"] = f"{type(ex).__name__}: {ex}"
 
     # ---- secondary: whole training steps of the three config models on the arxiv shape (cuBLAS GEMMs +
     # our sparse kernels + autograd: forward, backward, SGD), informational

@@ -103,27 +103,3 @@ def fused_gcn_layer(graph, x, weight, bias=None, relu=False):
     if graph.out_norm is not None or graph.in_norm is not None:
         raise NotImplementedError("fused GCN layer: graphs with separate in/out norms take the unfused path")
     return FusedGCNFunction.apply(_structure(graph), graph.raw_edge_weight, x, weight, bias, relu, graph.is_symmetric())
-
-
-def bench_fused_vs_unfused(torch_mod, st, w, x, bench):
-    """bench.py extras: one GCN layer 128 -> 128 (+bias, ReLU) on the arxiv shape, fused vs SpMM + cuBLAS."""
-    dev = x.device
-    lin = torch_mod.nn.Linear(128, 128).to(dev)
-    W, b = lin.weight.detach().contiguous(), lin.bias.detach().contiguous()
-    res = {}
-
-    def unfused_ref_order():       # the reference order: GEMM (+bias) first, then aggregate, then ReLU
-        return torch_mod.relu_(spmm_raw(st, w, torch_mod.addmm(b, x, W.t())))
-
-    def unfused_same_order():      # aggregate first, then GEMM + bias * rowsum + ReLU in torch
-        return torch_mod.relu_(spmm_raw(st, w, x) @ W.t())
-
-    bench("C2_gcn_layer_fused_tcgen05", lambda: fused_gcn_raw(st, w, x, W, b, True))
-    bench("C2_gcn_layer_unfused_gemm_then_spmm", unfused_ref_order)
-    bench("C2_gcn_layer_unfused_spmm_then_gemm", unfused_same_order)
-    a = fused_gcn_raw(st, w, x, W, b, True).double()
-    r = torch_mod.relu(torch_mod.sparse_csr_tensor(st.rowptr.long(), st.colind.long(), w.double(), size=(st.n_rows, st.n_cols))
-                       @ (x.double() @ W.double().t() + b.double()))
-    scale = torch_mod.maximum(r.abs(), r.abs().amax(dim=1, keepdim=True)).clamp_min(1e-30)
-    res["C2_gcn_layer_fused_max_rel_err_vs_fp64"] = float(((a - r).abs() / scale).max())
-    return res
