@@ -1,5 +1,6 @@
 #!/bin/bash
 # Multi-GPU measurement session (one box, N GPUs):  tools/run_multi_gpu.sh N [tag]
+#   tools/run_multi_gpu.sh N tag "weak_b005 strong_b005" runs a subset;
 #   weak scaling (default beta 0.05), the locality sweep beta in {0.25, 1.0}, strong scaling (papers100M / N),
 #   and the gloo-free NCCL parity that bench.py runs inside every configuration.  JSON lines land in gpurun_out/.
 set -u
@@ -14,10 +15,15 @@ run() {  # name, extra args...
   echo "== $name rc=$? $(head -c 400 $OUT/${TAG}_n${N}_${name}.json | cut -c1-300)"
   tail -c 300 $OUT/${TAG}_n${N}_${name}.err
 }
-run weak_b005 --steps 20 --warmup 3
-run weak_b025 --steps 10 --warmup 3 --beta 0.25
-run weak_b100 --steps 6 --warmup 3 --beta 1.0
-run strong_b005 --steps 10 --warmup 3 --scaling strong
+CONFIGS=${3:-"weak_b005 weak_b025 weak_b100 strong_b005"}
+for c in $CONFIGS; do
+  case $c in
+    weak_b005) run weak_b005 --steps 20 --warmup 3 ;;
+    weak_b025) run weak_b025 --steps 10 --warmup 3 --beta 0.25 ;;
+    weak_b100) run weak_b100 --steps 6 --warmup 3 --beta 1.0 ;;
+    strong_b005) run strong_b005 --steps 10 --warmup 3 --scaling strong ;;
+  esac
+done
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$OUT/${TAG}_n${N}_*.json")):
