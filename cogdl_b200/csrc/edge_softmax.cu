@@ -845,7 +845,7 @@ static int es_entry(const int32_t *rowptr, const float *a, const float *b, float
   return es_launch<MODE>(p, plan, (cudaStream_t)stream, who);
 }
 
-// GAT attention (used by gat_fused.cu): att = softmax_row(leakyrelu(h_l[row] + h_r[col])), any H.
+// GAT attention (used by cogdl_b200_gat_fwd_f32, mhspmm.cu): att = softmax_row(leakyrelu(h_l[row] + h_r[col])), any H.
 int gat_attention(const int32_t *rowptr, const int32_t *colind, const float *h_l, const float *h_r, float slope,
                   float *att, int64_t n_rows, int64_t H, const cogdl_b200_hub_plan_t *plan, cudaStream_t s) {
   EsParams p;
