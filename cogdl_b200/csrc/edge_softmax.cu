@@ -450,16 +450,19 @@ __global__ void __launch_bounds__(WARPS * 32) es_main_kernel(const EsParams p) {
             p.grow[(int64_t)grow_row * H + h] = acc;     // also the (empty-row) zero
           }
         } else {
-          float mx = -CUDART_INF_F;
-          for (int k = k0; k < k1; ++k) mx = fmaxf(mx, T[k * H + h]);
-          float s = 0.f;
+          // online max / sum (one pass, one exp per element: e = exp(-|x - m|) is the rescale factor of the running
+          // sum when x is a new maximum and the new term otherwise), then one normalising pass: 2 LDS + 1 STS and
+          // 2 MUFU per element instead of 3 LDS + 2 STS -- the kernel is issue-bound (profiles/)
+          float mx = -CUDART_INF_F, sm = 0.f;
           for (int k = k0; k < k1; ++k) {
-            const float ex = es_exp(T[k * H + h] - mx);
-            T[k * H + h] = ex;
-            s += ex;
+            const float x = T[k * H + h];
+            const float d = x - mx;
+            const float e = es_exp(-fabsf(d));
+            sm = (d > 0.f) ? fmaf(sm, e, 1.f) : sm + e;
+            mx = fmaxf(mx, x);
           }
-          const float inv = 1.f / s;
-          for (int k = k0; k < k1; ++k) T[k * H + h] = T[k * H + h] * inv;
+          const float inv = 1.f / sm;
+          for (int k = k0; k < k1; ++k) T[k * H + h] = es_exp(T[k * H + h] - mx) * inv;
         }
       }
     }
