@@ -14,19 +14,24 @@
 //
 // Work decomposition with a hub plan (round 2; one or two launches on the caller's stream, no side
 // stream, no events, no cluster kernel):
-//   items = hub CHUNKS (<= chunk_edges edges of one hub row) followed by SEGMENTS (runs of consecutive
-//   non-hub rows, ~seg_cost rows+edges), one warp per item -- the same items as the row-stream SpMM.
+//   items = SEGMENTS (runs of consecutive non-hub rows, ~seg_cost rows+edges) and hub CHUNKS (<= chunk_edges
+//   edges of one hub row), one warp per item -- the same items as the row-stream SpMM.
 //   * es_stats_kernel (only when the graph has hub rows): every chunk reduces its own (max, sum exp)
 //     per head; the last chunk of a row to arrive merges them IN CHUNK ORDER into the row's (M, S)
 //     (deterministic; a 22 K-edge hub is reduced by 350 warps on many SMs instead of serialising on
 //     one SM, and nobody spins waiting for anybody).
-//   * es_main_kernel: a chunk normalises its elements with its row's (M, S); a segment stages whole
+//   * es_main_kernel (launched as a PROGRAMMATIC DEPENDENT of the statistics kernel: it starts while that one is
+//     still running; segments come first in its grid and need nothing from it, chunk items come last and execute
+//     griddepcontrol.wait): a chunk normalises its elements with its row's (M, S); a segment stages whole
 //     rows in shared memory -- by ONE `cp.async.bulk` (TMA 1-D, UBLKCP) per window completed on an
 //     mbarrier when the tile is 16-byte aligned, else by coalesced loads --, computes max / sum exp /
 //     normalise per (row, head) pair held by one lane, and writes the tile back with one bulk store.
 //     Rows of a window are visited in DEGREE-SORTED order (one 32-key bitonic sort in registers), so the
 //     32/H rows a warp works on at a time have near-equal trip counts: on power-law rows (median 3
 //     edges, tail to 64) this is what removes the lane divergence that dominated round 1's kernel.
+//     (A register-resident variant -- every lane owning coalesced elements, two-level per-(row, head) folds, no
+//     staging, ~3x fewer instructions -- was built, validated and measured SLOWER, 89 vs 64 us at arxiv H=8: only
+//     24 warps/SM of 2 KB windows leave each window's latency chain exposed.  Removed)
 // Without a plan every row takes the warp path (es_warp_kernel); head counts that are not a power of
 // two, or > 32, use a generic strided kernel.
 //   MODE 0: forward, a = logits        MODE 1: backward, a = y, b = g  -> y * (g - sum_row y*g)
@@ -486,209 +491,6 @@ __global__ void __launch_bounds__(WARPS * 32) es_main_kernel(const EsParams p) {
   }
 }
 
-// ---------------------------------------------------------------- main kernel, register-resident segments
-// For tiles of <= KMAX * 32 floats (every H <= 16 with the default 64-edge chunks) nothing is staged at all:
-// lane L owns the window's elements L, L + 32, ... (fully coalesced 128-byte loads, all issued up front:
-// 2 * KMAX independent loads in flight per lane), i.e. ONE head (L % H) of every (32 / H)-th edge ("slot"
-// L / H).  Per-(row, head) reductions are two-level: each lane folds the run of its own elements that belong
-// to one row and drops one partial per (slot, row, head) into a small shared array (padded: conflict free);
-// a short (row, head)-per-lane pass folds the <= 32/H partials in slot order (deterministic) and leaves the
-// row statistic where every lane can read it.  All 32 lanes are busy whatever the degree distribution --
-// the staged kernel above gives one (row, head) pair to a lane, which on power-law rows is a 2-3x loss
-// (ncu, profiles/: 2.2 warp-instructions per element, issue-bound).  Results go straight to global memory.
-template <int MODE, int KMAX, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (KMAX <= 16 ? 6 : 3)) es_reg_kernel(const EsParams p) {
-  constexpr bool TWO = (MODE == 1 || MODE == 3);
-  constexpr int CAP = KMAX * 32;
-  __shared__ float SLA_all[WARPS][33 * 32];    // partial per (slot, row, head): index (slot * 33 + row) * H + head
-  __shared__ float RS_all[WARPS][32 * 32];     // merged statistic per (row, head):  index row * H + head
-  __shared__ int RP_all[WARPS][34];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t item = (int64_t)blockIdx.x * WARPS + wib;
-  const int H = p.H, lgH = p.lgH;
-  if (item < p.hub.n_chunks) {
-    es_chunk_item<MODE>(p, item, lane);
-    return;
-  }
-  const int64_t seg = item - p.hub.n_chunks;
-  if (seg >= p.hub.n_segs) return;
-  const int2 rr = __ldg(p.hub.segs + seg);
-  float *SLA = SLA_all[wib], *RS = RS_all[wib];
-  int *RP = RP_all[wib];
-  const int h = lane & (H - 1), slot = lane >> lgH, S = 32 >> lgH;
-  int rw = rr.x;
-  while (rw < rr.y) {
-    const int row = rw + lane;
-    const int base = __ldg(p.rowptr + rw);
-    int endl = 0x7fffffff;
-    if (row < rr.y) endl = __ldg(p.rowptr + row + 1);
-    const unsigned fit = __ballot_sync(FULL, row < rr.y && (int64_t)(endl - base) * H <= CAP);
-    const int m = __popc(fit);
-    if (m == 0) {                              // cannot happen when chunk_edges * H <= CAP (host check)
-      rw += 1;
-      continue;
-    }
-    const int e_end = __shfl_sync(FULL, endl, m - 1);
-    const int n = (e_end - base) * H;
-    if (lane < m) RP[lane + 1] = endl - base;
-    if (lane == 0) RP[0] = 0;
-    // ---- my elements: value(s) + local row id, everything issued before anything is used
-    float x[KMAX], g[TWO ? KMAX : 1];
-    unsigned rpk[KMAX / 4];     // local row id + 1 of element k, one byte each (0 = no element)
-#pragma unroll
-    for (int k = 0; k < KMAX / 4; ++k) rpk[k] = 0u;
-#define ES_ROW(k) ((int)((rpk[(k) >> 2] >> (((k) & 3) * 8)) & 0xffu) - 1)
-    const float *pa = p.a + (int64_t)base * H, *pb = TWO ? p.b + (int64_t)base * H : nullptr;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int idx = k * 32 + lane;
-      x[k] = 0.f;
-      if (TWO) g[k] = 0.f;
-      if (idx < n) {
-        rpk[k >> 2] |= (unsigned)(__ldg(p.hub.edge_row + base + (idx >> lgH)) - rw + 1) << ((k & 3) * 8);
-        if (MODE != 2) x[k] = ld_stream(pa + idx);
-        if (TWO) g[k] = ld_stream(pb + idx);
-      }
-    }
-    if (MODE == 2) {
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (ES_ROW(k) >= 0) {
-          const int c = __ldg(p.colind + base + ((k * 32 + lane) >> lgH));
-          const float z = __ldg(p.a + (int64_t)(rw + ES_ROW(k)) * H + h) + __ldg(p.b + (int64_t)c * H + h);
-          x[k] = z > 0.f ? z : z * p.slope;
-        }
-      }
-    }
-    __syncwarp();
-    // fold of the slot partials of one (row, head): slots touched by the row's edges, in slot order
-    auto merged = [&](int rl, int hh, bool is_max) {
-      const int k0 = RP[rl], deg = RP[rl + 1] - k0;
-      float acc = is_max ? -CUDART_INF_F : 0.f;
-      const int cnt = deg < S ? deg : S;
-      for (int j = 0; j < cnt; ++j) {
-        const int sl = deg < S ? ((k0 + j) & (S - 1)) : j;
-        const float v = SLA[(sl * 33 + rl) * H + hh];
-        acc = is_max ? fmaxf(acc, v) : acc + v;
-      }
-      return acc;
-    };
-    if (!TWO) {
-      // ---- pass 1: max
-      {
-        int cur = -1;
-        float mx = -CUDART_INF_F;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (ES_ROW(k) >= 0) {
-            if (ES_ROW(k) != cur) {
-              if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = mx;
-              cur = ES_ROW(k);
-              mx = x[k];
-            } else {
-              mx = fmaxf(mx, x[k]);
-            }
-          }
-        }
-        if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = mx;
-      }
-      __syncwarp();
-      for (int q = lane; q < m * H; q += 32) RS[q] = merged(q >> lgH, q & (H - 1), true);
-      __syncwarp();
-      // ---- pass 2: exp and sum
-      {
-        int cur = -1;
-        float sm = 0.f, mrow = 0.f;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (ES_ROW(k) >= 0) {
-            if (ES_ROW(k) != cur) {
-              if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
-              cur = ES_ROW(k);
-              sm = 0.f;
-              mrow = RS[cur * H + h];
-            }
-            x[k] = es_exp(x[k] - mrow);
-            sm += x[k];
-          }
-        }
-        if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
-      }
-      __syncwarp();
-      for (int q = lane; q < m * H; q += 32) RS[q] = 1.f / merged(q >> lgH, q & (H - 1), false);
-      __syncwarp();
-      // ---- pass 3: normalise, store
-      float *o = p.out + (int64_t)base * H;
-      {
-        int cur = -1;
-        float inv = 0.f;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (ES_ROW(k) >= 0) {
-            if (ES_ROW(k) != cur) { cur = ES_ROW(k); inv = RS[cur * H + h]; }
-            st_stream(o + k * 32 + lane, x[k] * inv);
-          }
-        }
-      }
-      __syncwarp();
-    } else {
-      // ---- pass 1: sum y * g
-      {
-        int cur = -1;
-        float sm = 0.f;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (ES_ROW(k) >= 0) {
-            if (ES_ROW(k) != cur) {
-              if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
-              cur = ES_ROW(k);
-              sm = 0.f;
-            }
-            sm = fmaf(x[k], g[k], sm);
-          }
-        }
-        if (cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
-      }
-      __syncwarp();
-      for (int q = lane; q < m * H; q += 32) RS[q] = merged(q >> lgH, q & (H - 1), false);
-      __syncwarp();
-      // ---- pass 2: y * (g - s) [* leakyrelu'], store; MODE 3 also folds the row sums of the result
-      float *o = p.out + (int64_t)base * H;
-      {
-        int cur = -1;
-        float srow = 0.f, hlrow = 0.f, sm = 0.f;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (ES_ROW(k) >= 0) {
-            if (ES_ROW(k) != cur) {
-              if (MODE == 3 && cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
-              cur = ES_ROW(k);
-              srow = RS[cur * H + h];
-              if (MODE == 3) { hlrow = __ldg(p.hl + (int64_t)(rw + cur) * H + h); sm = 0.f; }
-            }
-            float v = x[k] * (g[k] - srow);
-            if (MODE == 3) {
-              const int c = __ldg(p.colind + base + ((k * 32 + lane) >> lgH));
-              const float z = hlrow + __ldg(p.hr + (int64_t)c * H + h);
-              v *= (z > 0.f ? 1.f : p.slope);
-              sm += v;
-            }
-            st_stream(o + k * 32 + lane, v);
-          }
-        }
-        if (MODE == 3 && cur >= 0) SLA[(slot * 33 + cur) * H + h] = sm;
-      }
-      __syncwarp();
-      if (MODE == 3) {
-        for (int q = lane; q < m * H; q += 32) p.grow[(int64_t)rw * H + q] = merged(q >> lgH, q & (H - 1), false);  // empty rows: 0
-      }
-      __syncwarp();
-    }
-    rw += m;
-  }
-#undef ES_ROW
-}
-
 // ---------------------------------------------------------------- generic H: warp per row, loop over heads
 template <int MODE>
 __global__ void __launch_bounds__(256) es_generic_kernel(const EsParams p) {
@@ -804,26 +606,10 @@ static int es_launch(EsParams p, const cogdl_b200_hub_plan_t *plan, cudaStream_t
     es_stats_kernel<MODE><<<(unsigned)ceil_div((int64_t)p.hub.n_chunks * 32, 256), 256, 0, s>>>(p);
     CB_LAUNCH_CHECK();
   }
-  static int cap_floor = -1, use_reg = -1;
+  static int cap_floor = -1;
   if (cap_floor < 0) {
     const char *e = getenv("COGDL_B200_ES_CAP");   // tuning only: smallest tile (floats per warp) of the staged kernel
     cap_floor = e ? atoi(e) : 0;
-    const char *r = getenv("COGDL_B200_ES_REG");   // experiments: 1 selects the register-resident kernel (measured
-    use_reg = r ? atoi(r) : 0;                     // SLOWER on B200: 89 vs 64 us at arxiv H=8 -- fewer instructions, but
-                                                   // 24 warps/SM of 2 KB windows leave the per-window latency chain exposed)
-  }
-  if (use_reg && cap_need <= 1024) {
-    constexpr int RW = 4;
-    const int64_t items = (int64_t)p.hub.n_chunks + p.hub.n_segs;
-    const int64_t blocks = ceil_div(items, RW);
-    CB_REQUIRE(blocks <= 0x7fffffffLL, "%s: problem too large for one launch", who);
-    note_kernel("cogdl_b200::es_reg_kernel<MODE=%d,KMAX=%d,WARPS=4> (register-resident windows)", MODE, cap_need <= 512 ? 16 : 32);
-    if (blocks > 0) {
-      if (cap_need <= 512) es_reg_kernel<MODE, 16, RW><<<(unsigned)blocks, RW * 32, 0, s>>>(p);
-      else es_reg_kernel<MODE, 32, RW><<<(unsigned)blocks, RW * 32, 0, s>>>(p);
-      CB_LAUNCH_CHECK();
-    }
-    return COGDL_B200_OK;
   }
   const int64_t cap = cap_need > cap_floor ? cap_need : cap_floor;
   const int chosen = cap <= 512 ? 512 : (cap <= 1024 ? 1024 : 2048);

@@ -194,19 +194,13 @@ static int launch_spmm_stream(const SpmmParams &p, cudaStream_t stream) {
   const StreamParams q = to_stream(p);
   const int mode = p.val ? MODE_WEIGHTED : MODE_UNWEIGHTED;
   if constexpr (NV == 1 && sizeof(VecT) == 16) {
+    // lean loop (stream_range_lean); the variants differ in gathers per batch (U) and resident blocks per SM
     switch (spmm_variant()) {
-      case 0: return launch_stream<VecT, 1, 8, 1>(q, mode, stream);
-      case 2: return launch_stream<VecT, 1, 4, 5>(q, mode, stream);
-      case 3: return launch_stream<VecT, 1, 4, 6>(q, mode, stream);
-      case 4: return launch_stream<VecT, 1, 16, 2>(q, mode, stream);
-      case 5: return launch_stream<VecT, 1, 8, 4, false>(q, mode, stream);
-      case 6: return launch_stream<VecT, 1, 8, 3>(q, mode, stream);
-      case 1: return launch_stream<VecT, 1, 8, 4>(q, mode, stream);
-      case 8: return launch_stream<VecT, 1, 4, 5, false, true>(q, mode, stream);   // + L2 evict_last hint on X
-      case 10: return launch_stream<VecT, 1, 4, 4, false>(q, mode, stream);
-      case 11: return launch_stream<VecT, 1, 8, 3, false>(q, mode, stream);
-      case 12: return launch_stream<VecT, 1, 6, 4, false>(q, mode, stream);
-      // U=4, 48 registers (40 warps/SM), no slab prefetch: fastest measured (profiles/r01d_tune_stream_v2.txt)
+      case 1: return launch_stream<VecT, 1, 8, 4, false>(q, mode, stream);
+      case 2: return launch_stream<VecT, 1, 8, 3, false>(q, mode, stream);
+      case 3: return launch_stream<VecT, 1, 4, 6, false>(q, mode, stream);
+      case 8: return launch_stream<VecT, 1, 4, 5, false, true>(q, mode, stream);   // round-1 loop + L2 evict_last hint on X (slower)
+      // U=4, 48 registers (40 warps/SM): fastest measured (profiles/r01d_tune_stream_v2.txt, r02m_bench_n1.json)
       default: return launch_stream<VecT, 1, 4, 5, false>(q, mode, stream);
     }
   }
