@@ -39,6 +39,17 @@ void note_kernel(const char *fmt, ...);
     CB_CUDA(cudaPeekAtLastError());        \
   } while (0)
 
+// cudaFuncSetAttribute is per device: a once-flag per (kernel, device), device < 64.  Racing first calls from two
+// host threads set the attribute twice, which is harmless.  Returns the current device in *dev.
+static inline bool first_use_on_device(unsigned long long &mask, int *dev) {
+  *dev = 0;
+  if (cudaGetDevice(dev) != cudaSuccess || *dev < 0 || *dev >= 64) return true;
+  const unsigned long long bit = 1ull << *dev;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

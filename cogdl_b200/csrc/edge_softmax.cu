@@ -545,11 +545,10 @@ static int launch_main(const EsParams &p, cudaStream_t s) {
   constexpr bool TWO = (MODE == 1 || MODE == 3);
   constexpr int WARPS = 8;
   constexpr size_t smem = (size_t)WARPS * CAP * 4 * (TWO ? 2 : 1) + (size_t)WARPS * 34 * 4 + (size_t)WARPS * 8;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  if (first_use_on_device(attr_done, &dev))
     CB_CUDA(cudaFuncSetAttribute(es_main_kernel<MODE, CAP, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
   const int64_t items = (int64_t)p.hub.n_chunks + p.hub.n_segs;
   const int64_t blocks = ceil_div(items, WARPS);
   if (blocks == 0) return COGDL_B200_OK;

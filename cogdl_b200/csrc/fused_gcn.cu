@@ -511,15 +511,11 @@ extern "C" int cogdl_b200_gcn_fused_f32(const int32_t *rowptr, const int32_t *co
   p.hub_agg = hub_agg ? hub_agg : X; p.rowsum = rowsum; p.out = out; p.n_rows = (int)n_rows; p.Fout = (int)Fout;
   p.Npad = (int)((Fout + 15) / 16 * 16); p.chunk_edges = plan->chunk_edges; p.relu = relu;
   p.n_tiles = (int)ceil_div(n_rows, fg::TILE_M);
-  static int n_sms = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    CB_CUDA(cudaGetDevice(&dev));
-    CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  static unsigned long long attr_done = 0;
+  int dev = 0, n_sms = 148;
+  if (first_use_on_device(attr_done, &dev))
     CB_CUDA(cudaFuncSetAttribute(fg::gcn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fg::SMEM_BYTES));
-    attr_done = true;
-  }
+  CB_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   const int want = (p.n_tiles + fg::GROUPS - 1) / fg::GROUPS;
   const int grid = want < n_sms ? want : n_sms;
   note_kernel("cogdl_b200::fg::gcn_fused_kernel<2 groups x tile 64x%d, K=128, bf16x3 split, tcgen05.mma kind::f16>", p.Npad);

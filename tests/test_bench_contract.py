@@ -81,3 +81,36 @@ def test_cpu_thread_sweep_takes_the_fastest_median():
 
     best, res = bench.cpu_thread_sweep(call, lambda t: state.update(t=t), 8, reps=3)
     assert best == 4 and set(res) == {8, 4, 2} and state["t"] == 4
+
+
+def test_shard_generator_is_deterministic_local_and_sliceable():
+    import torch
+    from cogdl_b200 import synth
+
+    a = synth.shard_csr(1, 4, 5000, 60000, 0.05, seed=0)
+    b = synth.shard_csr(1, 4, 5000, 60000, 0.05, seed=0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    rp, col = a
+    assert int(rp[-1]) == 60000 == col.numel() and int(col.min()) >= 0 and int(col.max()) < 20000
+    remote = ((col < 5000) | (col >= 10000)).float().mean().item()
+    assert 0.02 < remote < 0.06                       # beta * (P - 1) / P = 0.0375
+    rp0, col0 = synth.shard_csr(2, 4, 5000, 60000, 0.0, seed=0)
+    assert int(col0.min()) >= 10000 and int(col0.max()) < 15000      # beta = 0: every column inside the own range
+    rps, cols = synth.shard_csr(0, 4, 5000, 60000, 0.05, seed=0, max_slice_edges=10000)
+    assert 10000 <= int(rps[-1]) == cols.numel() < 12000 and rps.numel() < 5001
+    full = synth.shard_csr(0, 4, 5000, 60000, 0.05, seed=0)[0]
+    assert torch.equal(rps, full[: rps.numel()])       # the slice keeps the full shard's degree law
+
+
+def test_elementwise_error_uses_the_row_scale():
+    import importlib
+
+    import numpy as np
+
+    bench = importlib.import_module("bench")
+    ref = np.array([[100.0, 1e-6, -50.0], [0.0, 0.0, 0.0]], np.float32)
+    got = ref.copy()
+    got[0, 1] += 5e-4                                   # tiny element of a large row: judged against the row scale
+    assert abs(bench.elementwise_err(got, ref) - 5e-6) < 1e-7
+    got[1, 2] = 1e-3                                    # an all-zero row has no scale to hide behind
+    assert bench.elementwise_err(got, ref) > 1.0
