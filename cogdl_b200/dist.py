@@ -13,10 +13,16 @@ rows are independent, so the only coupling is the gather of X rows owned by othe
                                  compute: Y_local = A_local @ [X_local ; X_halo]   (two-source SpMM,
                                           cogdl_b200_spmm_csr_f32_2src -- no concatenation copy)
 
-This is the pull form of the boundary exchange; the push form ("all-reduce of boundary partial
-sums", north star) moves the same order of bytes -- (#distinct remote rows) * 4F per rank -- but
-needs the column-sliced matrix and an extra reduction pass, so the pull form is what is built.
-There is no all-reduce on the data path: a row's sum is completed by exactly one rank.
+This is the pull form of the boundary exchange and the default: there is no reduction on the data
+path, a row's sum is completed by exactly one rank.
+
+The push form named in the north star ("reduce of boundary partial sums") is `PushSpMM` below: rank
+p keeps the COLUMN slice A[:, lo_p:hi_p], multiplies it by its own X shard, and the partial sums of
+destination rows owned by other ranks are reduce-scattered -- a ragged all-to-all of the packed
+boundary rows followed by an in-order add that is folded into the interior SpMM (the received
+partials are a second source of a two-source SpMM with unit weights).  Same order of bytes as the
+pull form ((#distinct boundary rows) * 4F per rank), two SpMM launches instead of one; kept for
+comparison (opt-in).
 """
 import torch
 import torch.distributed as dist
@@ -92,6 +98,13 @@ def _all_to_all(out, inp, out_splits, in_splits, group=None):
     backend = dist.get_backend(group)
     if backend == "nccl":
         dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+        return
+    if out.is_cuda or inp.is_cuda:
+        # gloo has no device point-to-point: stage through the host (tests that run two ranks on one GPU;
+        # a real multi-GPU job uses NCCL above)
+        out_h = torch.empty(out.shape, dtype=out.dtype)
+        _all_to_all(out_h, inp.cpu(), out_splits, in_splits, group)
+        out.copy_(out_h)
         return
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     outs = list(out.split(out_splits)) if sum(out_splits) else [out[:0]] * world
@@ -286,3 +299,174 @@ def synthetic_partition(rank, world, device, seed=0, rows=PAPERS_ROWS_PER_GPU, e
     else:
         ps.x_local = torch.randn(rows, hidden, device=device, generator=gen)
     return ps
+
+
+# =============================================================================================
+# Push form: reduce of boundary partial sums (the exchange the north star names)
+# =============================================================================================
+class PushPartition:
+    """What rank p holds in the push form (index arithmetic only; device agnostic).
+
+    Rank p owns destination rows AND source columns [lo_p, hi_p) and keeps every edge (r, c) whose
+    column it owns, i.e. the column slice A[:, lo_p:hi_p], as two CSR blocks:
+
+      boundary  B  [n_brow x n_local]  one row per DISTINCT destination row owned by another rank
+                                       (ascending global id => grouped by owner rank), columns local;
+                                       P = B @ X_local are the boundary partial sums this rank sends
+      combined  C  [n_local x (n_local + n_recv)]
+                                       row i = its interior edges in CSR order (columns < n_local),
+                                       then one unit-weight entry per received partial that belongs
+                                       to row i, in (source rank, position) order (columns
+                                       n_local + k) => Y_local = C @ [X_local ; R] completes the
+                                       sums in a fixed order: deterministic, no atomics.
+
+    `rows_global` must be non-decreasing inside every source rank's block (true for edges kept in
+    CSR order); `cols_global` all lie inside [lo_p, hi_p)."""
+
+    def __init__(self, rank, world, bounds, rows_global, cols_global, val, group=None, comm_device=None):
+        self.rank, self.world, self.bounds = rank, world, list(bounds)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        self.lo, self.hi, self.n_local = lo, hi, hi - lo
+        rows_global, cols_global = rows_global.to(torch.int64), cols_global.to(torch.int64)
+        dev = rows_global.device
+        if cols_global.numel() and (int(cols_global.min()) < lo or int(cols_global.max()) >= hi):
+            raise ValueError("push form: every edge kept by a rank must have its column inside the rank's own range")
+        self.weighted = val is not None
+        interior = (rows_global >= lo) & (rows_global < hi)
+        # ---- boundary block B
+        rb, cb = rows_global[~interior], cols_global[~interior] - lo
+        if rb.numel() > 1 and not bool((rb[1:] >= rb[:-1]).all()):
+            order = torch.sort(rb, stable=True).indices            # keeps the CSR order inside a destination row
+            rb, cb = rb[order], cb[order]
+            vb = None if val is None else val[~interior][order]
+        else:
+            vb = None if val is None else val[~interior]
+        self.brow, counts = torch.unique_consecutive(rb, return_counts=True)     # ascending global row ids
+        self.n_brow = int(self.brow.numel())
+        self.b_rowptr = torch.zeros(self.n_brow + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=self.b_rowptr[1:])
+        self.b_col, self.b_val = cb, vb
+        bt = torch.tensor(self.bounds, device=dev, dtype=torch.int64)
+        owner = torch.searchsorted(bt, self.brow, right=True) - 1
+        self.send_counts = torch.bincount(owner, minlength=world).tolist()       # partial rows I send to each rank
+        assert self.send_counts[rank] == 0
+        dest_local = self.brow - bt[owner]                                       # row inside the owner's shard
+        # ---- tell every owner which of its rows my partials belong to (once per structure)
+        cdev = dev if comm_device is None else comm_device
+        sc = torch.tensor(self.send_counts, dtype=torch.int64, device=cdev)
+        rc = torch.empty(world, dtype=torch.int64, device=cdev)
+        _all_to_all(rc, sc, [1] * world, [1] * world, group)
+        self.recv_counts = [int(v) for v in rc.tolist()]                         # partial rows I receive from each rank
+        self.n_recv = sum(self.recv_counts)
+        recv_row = torch.empty(self.n_recv, dtype=torch.int64, device=cdev)
+        _all_to_all(recv_row, dest_local.to(cdev).contiguous(), self.recv_counts, self.send_counts, group)
+        self.recv_row = recv_row.to(dev)                                         # local row of received partial k
+        if self.n_recv and (int(self.recv_row.min()) < 0 or int(self.recv_row.max()) >= self.n_local):
+            raise RuntimeError("push form: a peer sent a partial sum for a row this rank does not own")
+        # ---- combined block C: interior edges first, then the partial slots, row by row (stable sort)
+        ri, ci = rows_global[interior] - lo, cols_global[interior] - lo
+        n_int = int(ri.numel())
+        rows_c = torch.cat([ri, self.recv_row])
+        cols_c = torch.cat([ci, self.n_local + torch.arange(self.n_recv, device=dev, dtype=torch.int64)])
+        order = torch.sort(rows_c, stable=True).indices
+        self.c_col = cols_c[order]
+        self.c_rowptr = torch.zeros(self.n_local + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(torch.bincount(rows_c, minlength=self.n_local), 0, out=self.c_rowptr[1:])
+        if val is None:
+            self.c_val = None                     # unweighted kernel: a partial enters as 1.0 * r == r exactly
+        else:
+            self.c_val = torch.cat([val[interior].to(torch.float32),
+                                    torch.ones(self.n_recv, dtype=torch.float32, device=dev)])[order]
+        self.nnz_interior, self.nnz_boundary = n_int, int(cb.numel())
+
+    # -------------------------------------------------------------------- constructors
+    @staticmethod
+    def from_global_csr(row_ptr, col, val, rank, world, bounds=None, group=None, comm_device=None):
+        """Column slice of a replicated global CSR (host or device tensors), edges kept in CSR order."""
+        bounds = balanced_row_ranges(row_ptr, world) if bounds is None else bounds
+        lo, hi = bounds[rank], bounds[rank + 1]
+        col = col.to(torch.int64)
+        mine = ((col >= lo) & (col < hi)).nonzero().view(-1)
+        deg = (row_ptr[1:] - row_ptr[:-1]).to(torch.int64)
+        rows = torch.repeat_interleave(torch.arange(deg.numel(), device=col.device, dtype=torch.int64), deg)
+        return PushPartition(rank, world, bounds, rows[mine], col[mine], None if val is None else val[mine],
+                             group=group, comm_device=comm_device)
+
+    @staticmethod
+    def from_row_shard(rank, world, bounds, row_ptr_local, col_global, val_local, group=None, comm_device=None):
+        """From the ROW shard a rank already holds (rows [lo, hi), global column ids): every boundary edge
+        (r, c, v) is shipped once, at setup, to the rank that owns column c (ragged all-to-all of int64
+        pairs); received blocks arrive in source-rank order, each in its sender's CSR order."""
+        lo, hi = bounds[rank], bounds[rank + 1]
+        dev = col_global.device
+        cdev = dev if comm_device is None else comm_device
+        col_global = col_global.to(torch.int64)
+        deg = (row_ptr_local[1:] - row_ptr_local[:-1]).to(torch.int64)
+        rows = lo + torch.repeat_interleave(torch.arange(deg.numel(), device=dev, dtype=torch.int64), deg)
+        bt = torch.tensor(list(bounds), device=dev, dtype=torch.int64)
+        owner = torch.searchsorted(bt, col_global, right=True) - 1
+        away = owner != rank
+        order = torch.sort(owner[away], stable=True).indices                     # group by owner, CSR order inside
+        send = torch.stack([rows[away][order], col_global[away][order]], 1).contiguous()
+        sc_l = torch.bincount(owner[away], minlength=world).tolist()
+        sc = torch.tensor(sc_l, dtype=torch.int64, device=cdev)
+        rc = torch.empty(world, dtype=torch.int64, device=cdev)
+        _all_to_all(rc, sc, [1] * world, [1] * world, group)
+        rc_l = [int(v) for v in rc.tolist()]
+        recv = torch.empty((sum(rc_l), 2), dtype=torch.int64, device=cdev)
+        _all_to_all(recv.view(-1), send.to(cdev).view(-1), [2 * c for c in rc_l], [2 * c for c in sc_l], group)
+        recv = recv.to(dev)
+        rv = None
+        if val_local is not None:
+            rv = torch.empty(sum(rc_l), dtype=torch.float32, device=cdev)
+            _all_to_all(rv, val_local.to(torch.float32)[away][order].to(cdev).contiguous(), rc_l, sc_l, group)
+            rv = rv.to(dev)
+        # interior edges (mine, CSR order) + received boundary edges (source-rank order = ascending rows)
+        rows_all = torch.cat([rows[~away], recv[:, 0]])
+        cols_all = torch.cat([col_global[~away], recv[:, 1]])
+        val_all = None if val_local is None else torch.cat([val_local.to(torch.float32)[~away], rv])
+        return PushPartition(rank, world, bounds, rows_all, cols_all, val_all, group=group, comm_device=comm_device)
+
+
+class PushSpMM:
+    """The step of the push form:  P = B @ X_local  ->  reduce-scatter of the boundary partial sums
+    (ragged all-to-all over NCCL/NVLink)  ->  Y_local = C @ [X_local ; R]  (two-source SpMM; the unit-weight
+    columns of C add the received partials to their rows in a fixed order).  Both products run on the
+    row-stream SpMM kernel (cogdl_b200_spmm_csr_f32 / _2src); there is no other kernel and no atomic."""
+
+    def __init__(self, part: PushPartition, device, group=None):
+        self.part, self.device, self.group = part, device, group
+        self.mode = "push"
+        self.n_local = part.n_local
+        self.exchange = ("push: boundary partial sums reduce-scattered by a ragged all_to_all_single, added in "
+                         "(source rank, row) order inside the interior SpMM")
+        if device.type == "cuda":
+            self.st_b = CSRStructure.from_int64(part.b_rowptr.to(device), part.b_col.to(device), n_cols=part.n_local)
+            self.st_c = CSRStructure.from_int64(part.c_rowptr.to(device), part.c_col.to(device),
+                                                n_cols=part.n_local + part.n_recv)
+            self.st_b.plan, self.st_c.plan
+            self.val_b = None if part.b_val is None else part.b_val.to(device).float().contiguous()
+            self.val_c = None if part.c_val is None else part.c_val.to(device).float().contiguous()
+
+    def partials(self, x_local):
+        """P [n_brow, F]: this rank's contribution to rows owned by other ranks, packed in send order."""
+        from .operators._raw import spmm_raw
+
+        return spmm_raw(self.st_b, self.val_b, x_local)
+
+    def reduce_scatter(self, p_send, F):
+        """Ragged all-to-all of the packed partial rows; returns R [n_recv, F] in (source rank, row) order."""
+        part = self.part
+        r = torch.empty((part.n_recv, F), dtype=p_send.dtype, device=p_send.device)
+        _all_to_all(r.view(-1), p_send.contiguous().view(-1), [c * F for c in part.recv_counts],
+                    [c * F for c in part.send_counts], self.group)
+        return r
+
+    def combine(self, x_local, r):
+        from .operators._raw import spmm_2src_raw
+
+        return spmm_2src_raw(self.st_c, self.val_c, x_local, r)
+
+    def spmm(self, x_local):
+        F = x_local.shape[1]
+        return self.combine(x_local, self.reduce_scatter(self.partials(x_local), F))

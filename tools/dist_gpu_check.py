@@ -1,5 +1,6 @@
-"""torchrun script (N GPUs, NCCL): the node-range partitioned SpMM against the single-process oracle
-on a small locality-controlled graph.  Usage:
+"""torchrun script (N GPUs, NCCL): the node-range partitioned SpMM -- halo (NCCL all-to-all), fused NVLink
+gather (p2p) and push (reduce of boundary partial sums) forms -- against the single-process oracle on a small
+locality-controlled graph.  Usage:
    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_gpu_check.py
 """
 import os
@@ -39,6 +40,30 @@ def main():
         if not (err <= 1e-5 and exact):
             ok.zero_()
         print(f"[rank {rank}] mode={mode} rows [{lo},{hi}) halo {ps.n_halo} rel_err {err:.2e} unsplit_rows_bit_exact {exact}", flush=True)
+        dist.barrier()
+    # push form (reduce of boundary partial sums): both constructors, against the same oracle
+    bounds = cdist.balanced_row_ranges(rp, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    e0, e1 = int(rp[lo]), int(rp[hi])
+    x_local = X[lo:hi].to(dev).contiguous()
+    for how in ("global", "row_shard"):
+        if how == "global":
+            part = cdist.PushPartition.from_global_csr(rp, col, val, rank, world, bounds, comm_device=dev)
+        else:
+            part = cdist.PushPartition.from_row_shard(rank, world, bounds, (rp[lo:hi + 1] - e0).to(dev), col[e0:e1].to(dev),
+                                                      val[e0:e1].to(dev))
+        push = cdist.PushSpMM(part, dev)
+        y = push.spmm(x_local)
+        same = torch.equal(y, push.spmm(x_local))
+        torch.cuda.synchronize()
+        ref = full[lo:hi]
+        got = y.cpu().numpy()
+        scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=1, keepdims=True))
+        err = float((np.abs(got - ref) / np.maximum(scale, 1e-30)).max())
+        if not (err <= 1e-5 and same):
+            ok.zero_()
+        print(f"[rank {rank}] mode=push({how}) rows [{lo},{hi}) boundary rows sent {part.n_brow} received {part.n_recv} "
+              f"elementwise_err {err:.2e} deterministic {same}", flush=True)
         dist.barrier()
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
