@@ -86,8 +86,11 @@ def profiled_traffic(kernel_name):
         return None, "no committed ncu traffic summary (profiles/*_spmm_traffic.json)"
     with open(best) as f:
         d = json.load(f)
+    # the instantiation is everything up to the closing '>'; a launch-shape suffix (" block=64": same SASS, other
+    # threads per block) moves no DRAM bytes and is not part of the match
+    inst = kernel_name[: kernel_name.rfind(">") + 1] if ">" in kernel_name else kernel_name
     want = re.sub(r"\s+", "", d.get("launched_as", ""))
-    if want and want != re.sub(r"\s+", "", kernel_name):
+    if want and want != re.sub(r"\s+", "", inst):
         return None, f"{os.path.basename(best)} profiles {d.get('launched_as')}, but this run launched {kernel_name}"
     return int(d["dram_bytes_read"] + d["dram_bytes_write"]), os.path.relpath(best, ROOT)
 

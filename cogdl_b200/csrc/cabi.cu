@@ -5,6 +5,12 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
 
 namespace cogdl_b200 {
 
@@ -26,6 +32,30 @@ void note_kernel(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
+  va_end(ap);
+}
+
+static std::mutex g_tuning_mu;
+static std::map<std::string, int> g_tuning;
+int tuning(const char *env_name, int dflt) {
+  std::lock_guard<std::mutex> lock(g_tuning_mu);
+  auto it = g_tuning.find(env_name);
+  if (it != g_tuning.end()) return it->second;
+  const char *e = getenv(env_name);
+  const int v = (e && *e) ? atoi(e) : dflt;
+  g_tuning.emplace(env_name, v);
+  return v;
+}
+static void tuning_reload() {
+  std::lock_guard<std::mutex> lock(g_tuning_mu);
+  g_tuning.clear();
+}
+
+void append_kernel_note(const char *fmt, ...) {
+  const size_t n = strlen(g_kernel);
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_kernel + n, sizeof(g_kernel) - n, fmt, ap);
   va_end(ap);
 }
 
@@ -126,6 +156,20 @@ extern "C" const char *cogdl_b200_last_error(void) { return g_err; }
 extern "C" int64_t cogdl_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char *cogdl_b200_last_kernel(void) { return g_kernel; }
+
+extern "C" void cogdl_b200_reload_tuning(void) { tuning_reload(); }
+
+extern "C" int cogdl_b200_hub_plan_layout(int64_t *out, int n) {
+  typedef cogdl_b200_hub_plan_t P;
+  const int64_t v[] = {(int64_t)sizeof(P), offsetof(P, chunk_edges), offsetof(P, n_hub_rows), offsetof(P, n_chunks),
+                       offsetof(P, n_empty_rows), offsetof(P, hub_rows), offsetof(P, chunks), offsetof(P, counters),
+                       offsetof(P, partials), offsetof(P, partials_bytes), offsetof(P, seg_cost), offsetof(P, n_segs),
+                       offsetof(P, segs), offsetof(P, edge_row), offsetof(P, hub_degrees_host), offsetof(P, ticket)};
+  const int m = (int)(sizeof(v) / sizeof(v[0]));
+  int k = 0;
+  for (; out && k < m && k < n; ++k) out[k] = v[k];
+  return k;
+}
 
 extern "C" int cogdl_b200_check_device(void) {
   int dev = 0;

@@ -170,14 +170,7 @@ __global__ void __launch_bounds__(256) spmm_kernel(const SpmmParams p) {
 // the unroll depth / occupancy target of the F <= 128 instantiation; the default is the variant
 // measured fastest on B200 (profiles/).
 // ------------------------------------------------------------------------------------------
-static int spmm_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("COGDL_B200_SPMM_VARIANT");
-    v = e ? atoi(e) : 7;
-  }
-  return v;
-}
+static int spmm_variant() { return tuning("COGDL_B200_SPMM_VARIANT", 7); }
 
 static StreamParams to_stream(const SpmmParams &p) {
   StreamParams q;
@@ -236,11 +229,7 @@ static int dispatch_spmm(const SpmmParams &p, cudaStream_t s) {
   const bool stream = p.hub.n_segs > 0;
   // narrow rows (F = 40 -> 10 float4): the lean row-stream form with the idle lanes masked beats the sub-warp
   // row kernel once a row needs more than `stream_min_fv` vectors (measured, profiles/; tunable for experiments)
-  static int stream_min_fv = -1;
-  if (stream_min_fv < 0) {
-    const char *e = getenv("COGDL_B200_SPMM_STREAM_MINFV");
-    stream_min_fv = e ? atoi(e) : 9;
-  }
+  const int stream_min_fv = tuning("COGDL_B200_SPMM_STREAM_MINFV", 9);
   if (stream && fv >= stream_min_fv && fv <= 16) return launch_spmm_stream<VecT, 1>(p, s);
   if (fv <= 1) return launch_spmm<VecT, 1, 1>(p, s);
   if (fv <= 2) return launch_spmm<VecT, 2, 1>(p, s);

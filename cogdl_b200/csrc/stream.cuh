@@ -43,6 +43,12 @@ struct StreamParams {
 };
 
 enum { MODE_UNWEIGHTED = 0, MODE_WEIGHTED = 1, MODE_MULTIHEAD = 2 };
+// Default of COGDL_B200_STREAM_DYNAMIC: 0 = one warp per item (the measured default), 1 = persistent form
+constexpr int STREAM_DYNAMIC_DEFAULT = 0;
+constexpr int STREAM_BLOCK_DEFAULT = 256;
+// resident blocks per SM the persistent instantiation is compiled for (64 registers: the ticket loop around the
+// item body does not fit the 48 registers of the one-warp-per-item kernel without spilling into its gather loop)
+constexpr int DYN_MINB = 4;
 enum { SRC_ONE = 0, SRC_TWO = 1, SRC_PEERS = 2 };
 
 template <typename VecT> __device__ __forceinline__ VecT sk_zero();
@@ -220,20 +226,15 @@ __device__ __forceinline__ void stream_range_lean(const StreamParams &p, int e, 
   }
 }
 
-template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, int MINB, bool PREFETCH, bool HINT>
-__global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p) {
+// One work item (wid = item * S + slice) processed by one warp.
+template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, bool PREFETCH, bool HINT>
+__device__ __forceinline__ void stream_item(const StreamParams &p, const int64_t wid, const int lane, int2 *s_cv, int *s_r) {
   constexpr int TILE = 32 * NV;
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t item = (MODE == MODE_MULTIHEAD) ? wid / p.S : wid;
   const int slice = (MODE == MODE_MULTIHEAD) ? (int)(wid - item * p.S) : 0;
   VecT *Y = reinterpret_cast<VecT *>(p.Y);
   VecT *P = reinterpret_cast<VecT *>(p.hub.partials);
   constexpr bool LEAN = (NV == 1 && MODE != MODE_MULTIHEAD && !HINT);
-  __shared__ int2 s_cv_all[LEAN ? 8 : 1][32];
-  __shared__ int s_r_all[LEAN ? 8 : 1][32];
-  int2 *s_cv = s_cv_all[LEAN ? (threadIdx.x >> 5) : 0];
-  int *s_r = s_r_all[LEAN ? (threadIdx.x >> 5) : 0];
 
   // column tiles: the multi-head form owns exactly one 32-vector slice; the plain form loops over
   // the row in TILE-vector passes (one pass for F <= 128 * NV)
@@ -307,35 +308,111 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
   }
 }
 
+// DYN = false: one warp per item, grid = ceil(items / 8) blocks (a block's warp slots are only handed to the next
+// block when its slowest warp has retired).
+// DYN = true : persistent form -- the grid is sized to the resident warp slots (SMs x MINB blocks); a warp takes
+// its first item from its own index and every further one from a ticket counter in the plan
+// (hub.ticket[0]; items keep their order: hub chunks first, then segments), so a warp slot is never idle while
+// items remain, whatever the spread of item durations and hub merges.  hub.ticket[1] counts retired warps; the last
+// one leaves both words zero for the next launch.  Per-row arithmetic is untouched => bit-identical results.
+template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, int MINB, bool PREFETCH, bool HINT, bool DYN = false>
+__global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p) {
+  const int lane = threadIdx.x & 31;
+  constexpr bool LEAN = (NV == 1 && MODE != MODE_MULTIHEAD && !HINT);
+  __shared__ int2 s_cv_all[LEAN ? 8 : 1][32];
+  __shared__ int s_r_all[LEAN ? 8 : 1][32];
+  int2 *s_cv = s_cv_all[LEAN ? (threadIdx.x >> 5) : 0];
+  int *s_r = s_r_all[LEAN ? (threadIdx.x >> 5) : 0];
+  if constexpr (!DYN) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    stream_item<VecT, NV, MODE, HAS_PERM, SRC, U, PREFETCH, HINT>(p, wid, lane, s_cv, s_r);
+  } else {
+    const int total = (p.hub.n_chunks + p.hub.n_segs) * p.S;        // < 2^31: checked by the launcher
+    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+    int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+#pragma unroll 1
+    while (wid < total) {
+      // opaque copy of the lane index: keeps the per-item address arithmetic inside the item (hoisted out of this
+      // loop it would stay live across the whole body and push the 48-register kernel into spills)
+      int l = lane;
+      asm volatile("" : "+r"(l));
+      stream_item<VecT, NV, MODE, HAS_PERM, SRC, U, PREFETCH, HINT>(p, (int64_t)wid, l, s_cv, s_r);
+      int t = 0;
+      if (l == 0) t = atomicAdd(p.hub.ticket, 1);
+      wid = n_warps + __shfl_sync(FULL, t, 0);
+    }
+    if (lane == 0) {
+      const int done = atomicAdd(p.hub.ticket + 1, 1);    // every warp's last ticket was drawn before this
+      if (done == n_warps - 1) { atomicExch(p.hub.ticket, 0); atomicExch(p.hub.ticket + 1, 0); }
+    }
+  }
+}
+
 // Launch helper: picks the instantiation for (mode, perm, two-source); U / MINB fixed by the caller.
 template <typename VecT, int NV, int U, int MINB, bool PREFETCH = true, bool HINT = false>
 static int launch_stream(const StreamParams &p, int mode, cudaStream_t stream) {
   const int64_t warps = ((int64_t)p.hub.n_chunks + p.hub.n_segs) * p.S;
-  const int64_t blocks = ceil_div(warps * 32, 256);
+  // Threads per block (COGDL_B200_STREAM_BLOCK, default STREAM_BLOCK_DEFAULT): a launch parameter only -- the kernel
+  // indexes its per-warp slabs by warp-in-block and takes its item from the global warp index.  A block's warp slots
+  // are handed to the next block only when its SLOWEST warp has retired, and item durations spread (gathers that
+  // miss L2, hub merges), so smaller blocks keep more of the resident warp slots busy.
+  int bs = tuning("COGDL_B200_STREAM_BLOCK", STREAM_BLOCK_DEFAULT);
+  if (bs != 32 && bs != 64 && bs != 128) bs = 256;
+  const int64_t blocks = ceil_div(warps * 32, bs);
   if (blocks == 0) return COGDL_B200_OK;
   if (blocks > 0x7fffffffLL) return set_error(COGDL_B200_EINVAL, "stream kernel: problem too large for one launch");
   const unsigned g = (unsigned)blocks;
   const int src = p.n_peers > 0 ? SRC_PEERS : (p.n0 != INT64_MAX ? SRC_TWO : SRC_ONE);
+  // Persistent form with dynamic tickets (plan->ticket present; COGDL_B200_STREAM_DYNAMIC, see stream_kernel):
+  // built for the default lean SpMM instantiation only.
+  if constexpr (NV == 1 && U == 4 && MINB == 5 && !PREFETCH && !HINT) {
+    if (mode != MODE_MULTIHEAD && p.hub.ticket != nullptr && warps < 0x7fffffffLL &&
+        tuning("COGDL_B200_STREAM_DYNAMIC", STREAM_DYNAMIC_DEFAULT) != 0) {
+      const unsigned gd = (unsigned)ceil_div(warps * 32, 256);   // 8 warps per block, at most the resident slots
+      note_kernel("cogdl_b200::stream_kernel<%s,NV=%d,%s,%s,U=%d,MINB=%d,dynamic>", sizeof(VecT) == 16 ? "float4" : "float", NV,
+                  mode == MODE_WEIGHTED ? "weighted" : "unweighted",
+                  src == SRC_PEERS ? "SRC_PEERS" : (src == SRC_TWO ? "SRC_TWO" : "SRC_ONE"), U, DYN_MINB);
+#define CB_STREAM_DYN(M, S)                                                                               \
+  do {                                                                                                    \
+    constexpr auto K = stream_kernel<VecT, NV, M, false, S, U, DYN_MINB, PREFETCH, HINT, true>;               \
+    const unsigned gp = (unsigned)persistent_grid<K>();                                                   \
+    K<<<gd < gp ? gd : gp, 256, 0, stream>>>(p);                                                            \
+  } while (0)
+      if (mode == MODE_WEIGHTED) {
+        if (src == SRC_PEERS) CB_STREAM_DYN(MODE_WEIGHTED, SRC_PEERS);
+        else if (src == SRC_TWO) CB_STREAM_DYN(MODE_WEIGHTED, SRC_TWO);
+        else CB_STREAM_DYN(MODE_WEIGHTED, SRC_ONE);
+      } else {
+        if (src == SRC_PEERS) CB_STREAM_DYN(MODE_UNWEIGHTED, SRC_PEERS);
+        else if (src == SRC_TWO) CB_STREAM_DYN(MODE_UNWEIGHTED, SRC_TWO);
+        else CB_STREAM_DYN(MODE_UNWEIGHTED, SRC_ONE);
+      }
+#undef CB_STREAM_DYN
+      CB_LAUNCH_CHECK();
+      return COGDL_B200_OK;
+    }
+  }
   note_kernel("cogdl_b200::stream_kernel<%s,NV=%d,%s%s,%s,U=%d,MINB=%d%s%s>", sizeof(VecT) == 16 ? "float4" : "float", NV,
               mode == MODE_MULTIHEAD ? "multihead" : (mode == MODE_WEIGHTED ? "weighted" : "unweighted"),
               (mode == MODE_MULTIHEAD && p.perm) ? "+perm" : "",
               src == SRC_PEERS ? "SRC_PEERS" : (src == SRC_TWO ? "SRC_TWO" : "SRC_ONE"), U, MINB,
               PREFETCH ? ",prefetch" : "", HINT ? ",l2hint" : "");
+  if (bs != 256) append_kernel_note(" block=%d", bs);
   if (mode == MODE_MULTIHEAD) {
     if constexpr (NV == 1) {
-      if (p.perm) stream_kernel<VecT, 1, MODE_MULTIHEAD, true, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-      else stream_kernel<VecT, 1, MODE_MULTIHEAD, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+      if (p.perm) stream_kernel<VecT, 1, MODE_MULTIHEAD, true, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
+      else stream_kernel<VecT, 1, MODE_MULTIHEAD, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
     } else {
       return set_error(COGDL_B200_EINVAL, "stream kernel: multi-head form needs NV == 1");
     }
   } else if (mode == MODE_WEIGHTED) {
-    if (src == SRC_PEERS) stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_PEERS, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-    else if (src == SRC_TWO) stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_TWO, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-    else stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    if (src == SRC_PEERS) stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_PEERS, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
+    else if (src == SRC_TWO) stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_TWO, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
+    else stream_kernel<VecT, NV, MODE_WEIGHTED, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
   } else {
-    if (src == SRC_PEERS) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_PEERS, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-    else if (src == SRC_TWO) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_TWO, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
-    else stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, 256, 0, stream>>>(p);
+    if (src == SRC_PEERS) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_PEERS, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
+    else if (src == SRC_TWO) stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_TWO, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
+    else stream_kernel<VecT, NV, MODE_UNWEIGHTED, false, SRC_ONE, U, MINB, PREFETCH, HINT><<<g, bs, 0, stream>>>(p);
   }
   CB_LAUNCH_CHECK();
   return COGDL_B200_OK;

@@ -7,8 +7,8 @@
  * the CogDL tree).  Differences from the reference ABI, all deliberate:
  *   - plain C: raw device pointers + int64 sizes + an opaque stream handle, no torch types;
  *   - the caller owns every buffer (outputs included); no device memory is allocated here (the
- *     reference leaks a cusparseHandle and cudaMalloc's per call, spmm_kernel.cu:517-531); the only
- *     persistent objects are one side stream + two events per device used by the edge-softmax tiers;
+ *     reference leaks a cusparseHandle and cudaMalloc's per call, spmm_kernel.cu:517-531); the library
+ *     keeps no streams or events of its own;
  *   - work is enqueued on the caller's stream (the reference uses the legacy default stream);
  *   - errors are returned (0 = ok, <0 = COGDL_B200_E*), text via cogdl_b200_last_error();
  *     the reference `assert`s / exit(1)s (spmm.cpp:28-39, computeUtil.h:13-27);
@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define COGDL_B200_ABI_VERSION 4
+#define COGDL_B200_ABI_VERSION 5
 
 #define COGDL_B200_OK 0
 #define COGDL_B200_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
@@ -58,6 +58,9 @@ COGDL_B200_API int64_t cogdl_b200_launch_count(void);
  * thread (e.g. "stream_kernel<float4,NV=1,weighted,SRC_ONE,U=4>"); "" before the first call.  Lets a
  * harness check that a profile it cites is of the kernel that actually ran. */
 COGDL_B200_API const char *cogdl_b200_last_kernel(void);
+/* Experiment knobs (environment variables COGDL_B200_*: kernel variants, tile floors) are read once and cached;
+ * this drops the cache so that a tuning sweep can change them inside one process.  Not needed in normal use. */
+COGDL_B200_API void cogdl_b200_reload_tuning(void);
 
 /* ---------------------------------------------------------------------------------------
  * Hub plan: how rows with more than `chunk_edges` edges are cut into fixed-size edge chunks
@@ -101,7 +104,16 @@ typedef struct cogdl_b200_hub_plan {
    * as many blocks / clusters as there are rows in a tier.  NULL => such ops treat every hub row
    * with the per-warp tier. */
   const int32_t *hub_degrees_host;
+  /* Optional (ABI 5): two ints of device memory, zero on entry, left zero on exit -- work-ticket and retirement
+   * counters of the PERSISTENT form of the row-stream kernels (grid = resident warp slots; a warp draws its next
+   * item from ticket[0] instead of retiring).  NULL => one warp per item.  Per-stream scratch like `counters`. */
+  int32_t *ticket;
 } cogdl_b200_hub_plan_t;
+
+/* Layout self-check for bindings that mirror the struct (ctypes, cgo, JNI): writes sizeof(cogdl_b200_hub_plan_t)
+ * to out[0] and the byte offset of each field, in declaration order, to out[1..]; returns the number of values
+ * written (at most n). */
+COGDL_B200_API int cogdl_b200_hub_plan_layout(int64_t *out, int n);
 
 /* Pass 1: counts_dev[0..3] = #rows with degree > chunk_edges, #chunks, #empty rows, #segments
  * (for seg_cost; pass seg_cost <= 0 to skip segments).  counts_dev: 4-int device buffer. */

@@ -114,3 +114,18 @@ def test_elementwise_error_uses_the_row_scale():
     assert abs(bench.elementwise_err(got, ref) - 5e-6) < 1e-7
     got[1, 2] = 1e-3                                    # an all-zero row has no scale to hide behind
     assert bench.elementwise_err(got, ref) > 1.0
+
+
+def test_profiled_traffic_matches_the_instantiation_not_the_launch_shape():
+    """roofline.traffic comes from a committed ncu capture and is only used when the capture is of the kernel
+    instantiation that ran; a launch-shape suffix after the closing '>' (threads per block) is not part of it."""
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    bench = importlib.import_module("bench")
+    name = "cogdl_b200::stream_kernel<float4,NV=1,weighted,SRC_ONE,U=4,MINB=5>"
+    t0, src0 = bench.profiled_traffic(name)
+    t1, src1 = bench.profiled_traffic(name + " block=64")
+    assert t0 is not None and t0 == t1 and src0 == src1 and t0 > 100e6
+    t2, why = bench.profiled_traffic("cogdl_b200::stream_kernel<float4,NV=1,weighted,SRC_ONE,U=4,MINB=4,dynamic>")
+    assert t2 is None and "launched" in why

@@ -157,7 +157,7 @@ def test_cabi_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/cogdl_b200.h but not exported"
     lib.cogdl_b200_abi_version.restype = ctypes.c_int
-    assert lib.cogdl_b200_abi_version() == 4
+    assert lib.cogdl_b200_abi_version() == 5
 
 
 def test_python_binding_lists_exactly_the_header_symbols():
