@@ -40,9 +40,10 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def knobs(block=256, dynamic=0):
+def knobs(block=256, dynamic=0, variant=7):
     os.environ["COGDL_B200_STREAM_BLOCK"] = str(block)
     os.environ["COGDL_B200_STREAM_DYNAMIC"] = str(dynamic)
+    os.environ["COGDL_B200_SPMM_VARIANT"] = str(variant)
     _cabi.load().cogdl_b200_reload_tuning()
 
 
@@ -65,9 +66,11 @@ def sweep(tag, st_by_seg, fn_of_st, shapes, reps):
     """shapes: list of (block, dynamic).  Reference output = first seg, block 256, dynamic 0."""
     ref = None
     for seg, st in st_by_seg.items():
-        for block, dyn in shapes:
+        for shape in shapes:
+            block, dyn = shape[0], shape[1]
+            variant = shape[2] if len(shape) > 2 else 7
             try:
-                knobs(block, dyn)
+                knobs(block, dyn, variant)
                 y = fn_of_st(st)
                 torch.cuda.synchronize()
                 if ref is None:
@@ -76,7 +79,7 @@ def sweep(tag, st_by_seg, fn_of_st, shapes, reps):
                 close = float((y - ref).abs().max() / ref.abs().max())
                 med, mn = timed(lambda: fn_of_st(st), reps)
                 clean = int(st.plan.counters.abs().sum()) == 0 and int(st.plan.ticket.abs().sum()) == 0
-                emit(case=tag, seg=seg, block=block, dynamic=dyn, median_us=round(med, 1), min_us=round(mn, 1),
+                emit(case=tag, seg=seg, block=block, dynamic=dyn, variant=variant, median_us=round(med, 1), min_us=round(mn, 1),
                      bit_identical_to_default=same, max_rel_vs_default=close, counters_clean=clean,
                      kernel=_cabi.last_kernel(), segs=st.plan.n_segs, chunks=st.plan.n_chunks)
             except Exception as ex:  # noqa: BLE001
@@ -99,12 +102,54 @@ emit(case="setup", arxiv_nnz=sts[128].nnz, gpu=torch.cuda.get_device_name(0))
 for F in (128, 40, 256):
     x = torch.randn(n, F, device=dev)
     sweep(f"arxiv_spmm_F{F}", sts if F == 128 else {128: sts[128]}, lambda st: spmm_raw(st, w, x), shapes, 30 if F == 128 else 15)
+    if F == 128 and what != "dynamic":
+        # other unroll / occupancy variants of the lean kernel at the two extreme block sizes
+        sweep("arxiv_spmm_F128_variants", {128: sts[128]}, lambda st: spmm_raw(st, w, x),
+              [(256, 0, 7), (256, 0, 3), (64, 0, 3), (256, 0, 1), (64, 0, 1)], 20)
+        # hub chunk size (edges per chunk); the plan is per structure
+        for chunk in (32, 128):
+            stc = CSRStructure(rp32, col32, n_cols=n, chunk_edges=chunk, seg_cost=128)
+            stc.plan
+            sweep(f"arxiv_spmm_F128_chunk{chunk}", {128: stc}, lambda st: spmm_raw(st, w, x), [(256, 0), (64, 0)], 20)
+            del stc
     del x
 H = 8
-att = torch.rand(sts[128].nnz, H, device=dev)
-h = torch.randn(n, H, 128, device=dev)
-sweep("arxiv_mhspmm_H8_F128", {128: sts[128]}, lambda st: mhspmm_raw(st, att, h), [s for s in shapes if s[1] == 0], 8)
-del att, h, sts
+if what != "dynamic":
+    # ---- edge softmax family (arxiv, H = 8): warps per block of the staged main kernel
+    from cogdl_b200.operators._raw import edge_softmax_bwd_raw, edge_softmax_fwd_raw, gat_attn_bwd_raw  # noqa: E402
+
+    st = sts[128]
+    logits = (torch.randn(st.nnz, H, device=dev) * 3).clamp_(-10, 10)
+    g = torch.randn(st.nnz, H, device=dev)
+    hl, hr = torch.randn(n, H, device=dev), torch.randn(n, H, device=dev)
+    os.environ["COGDL_B200_ES_WARPS"] = "8"
+    _cabi.load().cogdl_b200_reload_tuning()
+    att0 = edge_softmax_fwd_raw(st, logits)
+    for name, fn in (("es_fwd", lambda: edge_softmax_fwd_raw(st, logits)), ("es_bwd", lambda: edge_softmax_bwd_raw(st, att0, g)),
+                     ("gat_attn_bwd", lambda: gat_attn_bwd_raw(st, att0, g, hl, hr, 0.2)[0])):
+        ref = None
+        for warps in (8, 4, 2):
+            try:
+                os.environ["COGDL_B200_ES_WARPS"] = str(warps)
+                _cabi.load().cogdl_b200_reload_tuning()
+                y = fn()
+                torch.cuda.synchronize()
+                ref = y.clone() if ref is None else ref
+                med, mn = timed(fn, 20)
+                emit(case=f"arxiv_{name}_H8", es_warps=warps, median_us=round(med, 1), min_us=round(mn, 1),
+                     bit_identical_to_default=bool(torch.equal(y, ref)), counters_clean=int(st.plan.counters.abs().sum()) == 0,
+                     kernel=_cabi.last_kernel())
+            except Exception as ex:  # noqa: BLE001
+                emit(case=f"arxiv_{name}_H8", es_warps=warps, error=f"{type(ex).__name__}: {ex}")
+    os.environ["COGDL_B200_ES_WARPS"] = "8"
+    _cabi.load().cogdl_b200_reload_tuning()
+    del logits, g, hl, hr, att0
+if what != "dynamic":
+    att = torch.rand(sts[128].nnz, H, device=dev)
+    h = torch.randn(n, H, 128, device=dev)
+    sweep("arxiv_mhspmm_H8_F128", {128: sts[128]}, lambda st: mhspmm_raw(st, att, h), [s for s in shapes if s[1] == 0], 8)
+    del att, h
+del sts
 
 # ---- products shape (X >> L2, HBM-bound): unweighted SpMM F = 128
 n, e = synth.SHAPES["products"]
