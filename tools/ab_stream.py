@@ -87,8 +87,8 @@ def sweep(tag, st_by_seg, fn_of_st, shapes, reps):
     knobs()
 
 
-shapes = {"safe": [(256, 0), (128, 0), (64, 0), (32, 0)], "dynamic": [(256, 0), (256, 1)],
-          "all": [(256, 0), (128, 0), (64, 0), (32, 0), (256, 1)]}[what]
+SAFE, DYN = [(256, 0), (128, 0), (64, 0), (32, 0)], [(256, 0), (256, 1)]
+shapes = DYN if what == "dynamic" else SAFE     # "all": the safe shapes first, the persistent form at the very end
 
 # ---- arxiv shape (headline): weighted SpMM, F = 128 / 40 / 256; multi-head SpMM H = 8, F = 128
 n, e = synth.SHAPES["arxiv"]
@@ -149,7 +149,6 @@ if what != "dynamic":
     h = torch.randn(n, H, 128, device=dev)
     sweep("arxiv_mhspmm_H8_F128", {128: sts[128]}, lambda st: mhspmm_raw(st, att, h), [s for s in shapes if s[1] == 0], 8)
     del att, h
-del sts
 
 # ---- products shape (X >> L2, HBM-bound): unweighted SpMM F = 128
 n, e = synth.SHAPES["products"]
@@ -159,4 +158,13 @@ del rp, col
 st.plan
 x = torch.randn(n, 128, device=dev)
 sweep("products_spmm_F128", {128: st}, lambda s_: spmm_raw(s_, None, x), shapes, 6)
-emit(case="done")
+emit(case="safe_done" if what != "dynamic" else "done")
+if what == "all":
+    # ---- persistent form last: everything above is already on disk should this part misbehave
+    sweep("products_spmm_F128_dynamic", {128: st}, lambda s_: spmm_raw(s_, None, x), DYN, 6)
+    del x, st
+    for F in (128, 40):
+        x = torch.randn(sts[128].n_rows, F, device=dev)
+        sweep(f"arxiv_spmm_F{F}_dynamic", sts if F == 128 else {128: sts[128]}, lambda st_: spmm_raw(st_, w, x), DYN, 30)
+        del x
+    emit(case="done")
