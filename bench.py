@@ -744,22 +744,11 @@ def run_ours(args):
         # ---- parity of what was just timed, against the oracle (outside the timed regions)
         parity = parity_single(torch, rp, col, w, x_host, step(), st.chunk_edges)
         # ---- end to end: pinned host X -> device, spmm through the public API, Y -> pinned host
-        # The pinned buffers are allocated (and the copies issued) from the GPU's own NUMA node: on a two-socket
-        # host a process that happens to sit on the other socket pays the inter-socket link on every PCIe copy
-        # (measured 36 vs 45 GB/s between two otherwise identical runs).  The affinity is restored afterwards, so
-        # the CPU baseline leg below keeps all the host cores.
-        affinity = os.sched_getaffinity(0)
-        numa = bind_to_gpu_numa(torch, local)
         x_pin = x_host.pin_memory()
         x_in = torch.empty_like(x_dev)
         l1 = _cabi.launch_count()
         e2e_steps = args.steps
         ms_e2e = time_e2e(torch, dev, x_pin, x_in, lambda xi: cogdl_b200.spmm(g, xi), n, e2e_steps, args.warmup, False)
-        try:
-            os.sched_setaffinity(0, affinity)
-        except OSError:
-            pass
-        extra_keys["numa"] = numa
         clocks = sampler.stop()      # sampled across both timed regions
         launches = launches_dev + (_cabi.launch_count() - l1)
         total_units = nnz

@@ -37,7 +37,6 @@ class HubPlanStruct(ctypes.Structure):
         ("segs", ctypes.c_void_p),
         ("edge_row", ctypes.c_void_p),
         ("hub_degrees_host", ctypes.c_void_p),
-        ("ticket", ctypes.c_void_p),
     ]
 
 

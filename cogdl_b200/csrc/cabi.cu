@@ -164,7 +164,7 @@ extern "C" int cogdl_b200_hub_plan_layout(int64_t *out, int n) {
   const int64_t v[] = {(int64_t)sizeof(P), offsetof(P, chunk_edges), offsetof(P, n_hub_rows), offsetof(P, n_chunks),
                        offsetof(P, n_empty_rows), offsetof(P, hub_rows), offsetof(P, chunks), offsetof(P, counters),
                        offsetof(P, partials), offsetof(P, partials_bytes), offsetof(P, seg_cost), offsetof(P, n_segs),
-                       offsetof(P, segs), offsetof(P, edge_row), offsetof(P, hub_degrees_host), offsetof(P, ticket)};
+                       offsetof(P, segs), offsetof(P, edge_row), offsetof(P, hub_degrees_host)};
   const int m = (int)(sizeof(v) / sizeof(v[0]));
   int k = 0;
   for (; out && k < m && k < n; ++k) out[k] = v[k];

@@ -54,22 +54,6 @@ static inline bool first_use_on_device(unsigned long long &mask, int *dev) {
   return true;
 }
 
-// Blocks of `Kernel` (256 threads, no dynamic shared memory) that are resident at once on the current device:
-// the grid of a persistent launch.  Cached per (kernel, device).
-template <auto Kernel>
-static int persistent_grid() {
-  static int cached[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-  if (cached[dev] == 0) {
-    int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, 256, 0) != cudaSuccess) per_sm = 1;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-    cached[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
-  }
-  return cached[dev];
-}
-
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -84,18 +68,16 @@ struct HubView {
   const int2 *segs;      // (row_begin, row_end), hub-free
   const int *edge_row;
   int n_empty_rows;
-  int *ticket;           // 2 ints, zero between launches (persistent row-stream form); nullptr => one warp per item
 };
 
 static inline HubView hub_view(const cogdl_b200_hub_plan_t *plan) {
-  HubView h{0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr};
+  HubView h{0, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0};
   if (plan && plan->chunk_edges > 0) {
     h.chunk_edges = plan->chunk_edges;
     h.n_chunks = plan->n_chunks;
     h.chunks = reinterpret_cast<const int2 *>(plan->chunks);
     h.counters = plan->counters;
     h.partials = plan->partials;
-    h.ticket = plan->ticket;
     if (plan->segs && plan->edge_row && plan->n_segs > 0) {
       h.n_segs = plan->n_segs;
       h.segs = reinterpret_cast<const int2 *>(plan->segs);

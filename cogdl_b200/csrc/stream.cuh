@@ -43,12 +43,10 @@ struct StreamParams {
 };
 
 enum { MODE_UNWEIGHTED = 0, MODE_WEIGHTED = 1, MODE_MULTIHEAD = 2 };
-// Default of COGDL_B200_STREAM_DYNAMIC: 0 = one warp per item (the measured default), 1 = persistent form
-constexpr int STREAM_DYNAMIC_DEFAULT = 0;
-constexpr int STREAM_BLOCK_DEFAULT = 256;
-// resident blocks per SM the persistent instantiation is compiled for (64 registers: the ticket loop around the
-// item body does not fit the 48 registers of the one-warp-per-item kernel without spilling into its gather loop)
-constexpr int DYN_MINB = 4;
+// Threads per block of every row-stream launch (COGDL_B200_STREAM_BLOCK overrides): measured on B200
+// (profiles/r02s_ab_launch_shapes.md) 128 vs 256: F=256 253 -> 216 us, F=40 68.6 -> 66.6, mh-SpMM 981 -> 962,
+// products F=128 4769 -> 4718, arxiv F=128 unchanged; all outputs bit-identical.
+constexpr int STREAM_BLOCK_DEFAULT = 128;
 enum { SRC_ONE = 0, SRC_TWO = 1, SRC_PEERS = 2 };
 
 template <typename VecT> __device__ __forceinline__ VecT sk_zero();
@@ -308,14 +306,7 @@ __device__ __forceinline__ void stream_item(const StreamParams &p, const int64_t
   }
 }
 
-// DYN = false: one warp per item, grid = ceil(items / 8) blocks (a block's warp slots are only handed to the next
-// block when its slowest warp has retired).
-// DYN = true : persistent form -- the grid is sized to the resident warp slots (SMs x MINB blocks); a warp takes
-// its first item from its own index and every further one from a ticket counter in the plan
-// (hub.ticket[0]; items keep their order: hub chunks first, then segments), so a warp slot is never idle while
-// items remain, whatever the spread of item durations and hub merges.  hub.ticket[1] counts retired warps; the last
-// one leaves both words zero for the next launch.  Per-row arithmetic is untouched => bit-identical results.
-template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, int MINB, bool PREFETCH, bool HINT, bool DYN = false>
+template <typename VecT, int NV, int MODE, bool HAS_PERM, int SRC, int U, int MINB, bool PREFETCH, bool HINT>
 __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p) {
   const int lane = threadIdx.x & 31;
   constexpr bool LEAN = (NV == 1 && MODE != MODE_MULTIHEAD && !HINT);
@@ -323,39 +314,21 @@ __global__ void __launch_bounds__(256, MINB) stream_kernel(const StreamParams p)
   __shared__ int s_r_all[LEAN ? 8 : 1][32];
   int2 *s_cv = s_cv_all[LEAN ? (threadIdx.x >> 5) : 0];
   int *s_r = s_r_all[LEAN ? (threadIdx.x >> 5) : 0];
-  if constexpr (!DYN) {
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    stream_item<VecT, NV, MODE, HAS_PERM, SRC, U, PREFETCH, HINT>(p, wid, lane, s_cv, s_r);
-  } else {
-    const int total = (p.hub.n_chunks + p.hub.n_segs) * p.S;        // < 2^31: checked by the launcher
-    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
-    int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-#pragma unroll 1
-    while (wid < total) {
-      // opaque copy of the lane index: keeps the per-item address arithmetic inside the item (hoisted out of this
-      // loop it would stay live across the whole body and push the 48-register kernel into spills)
-      int l = lane;
-      asm volatile("" : "+r"(l));
-      stream_item<VecT, NV, MODE, HAS_PERM, SRC, U, PREFETCH, HINT>(p, (int64_t)wid, l, s_cv, s_r);
-      int t = 0;
-      if (l == 0) t = atomicAdd(p.hub.ticket, 1);
-      wid = n_warps + __shfl_sync(FULL, t, 0);
-    }
-    if (lane == 0) {
-      const int done = atomicAdd(p.hub.ticket + 1, 1);    // every warp's last ticket was drawn before this
-      if (done == n_warps - 1) { atomicExch(p.hub.ticket, 0); atomicExch(p.hub.ticket + 1, 0); }
-    }
-  }
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  stream_item<VecT, NV, MODE, HAS_PERM, SRC, U, PREFETCH, HINT>(p, wid, lane, s_cv, s_r);
 }
 
 // Launch helper: picks the instantiation for (mode, perm, two-source); U / MINB fixed by the caller.
 template <typename VecT, int NV, int U, int MINB, bool PREFETCH = true, bool HINT = false>
 static int launch_stream(const StreamParams &p, int mode, cudaStream_t stream) {
   const int64_t warps = ((int64_t)p.hub.n_chunks + p.hub.n_segs) * p.S;
-  // Threads per block (COGDL_B200_STREAM_BLOCK, default STREAM_BLOCK_DEFAULT): a launch parameter only -- the kernel
-  // indexes its per-warp slabs by warp-in-block and takes its item from the global warp index.  A block's warp slots
-  // are handed to the next block only when its SLOWEST warp has retired, and item durations spread (gathers that
-  // miss L2, hub merges), so smaller blocks keep more of the resident warp slots busy.
+  // Threads per block: a launch parameter only -- the kernel indexes its per-warp slabs by warp-in-block and takes its
+  // item from the global warp index, so every block size runs the same SASS and gives the same bits.  A block's warp
+  // slots go to the next block only when its SLOWEST warp has retired; item durations spread (gathers that miss L2,
+  // hub merges), so smaller blocks keep more warp slots busy -- most visibly for the two-vectors-per-lane
+  // instantiation (F = 256).  A persistent form (grid = resident warp slots, items drawn from a ticket counter in the
+  // plan) was also built and measured: slower (107 vs 101 us at arxiv F=128: the ticket loop needs 64 registers =
+  // 32 warps/SM) -- removed.
   int bs = tuning("COGDL_B200_STREAM_BLOCK", STREAM_BLOCK_DEFAULT);
   if (bs != 32 && bs != 64 && bs != 128) bs = 256;
   const int64_t blocks = ceil_div(warps * 32, bs);
@@ -363,35 +336,6 @@ static int launch_stream(const StreamParams &p, int mode, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL) return set_error(COGDL_B200_EINVAL, "stream kernel: problem too large for one launch");
   const unsigned g = (unsigned)blocks;
   const int src = p.n_peers > 0 ? SRC_PEERS : (p.n0 != INT64_MAX ? SRC_TWO : SRC_ONE);
-  // Persistent form with dynamic tickets (plan->ticket present; COGDL_B200_STREAM_DYNAMIC, see stream_kernel):
-  // built for the default lean SpMM instantiation only.
-  if constexpr (NV == 1 && U == 4 && MINB == 5 && !PREFETCH && !HINT) {
-    if (mode != MODE_MULTIHEAD && p.hub.ticket != nullptr && warps < 0x7fffffffLL &&
-        tuning("COGDL_B200_STREAM_DYNAMIC", STREAM_DYNAMIC_DEFAULT) != 0) {
-      const unsigned gd = (unsigned)ceil_div(warps * 32, 256);   // 8 warps per block, at most the resident slots
-      note_kernel("cogdl_b200::stream_kernel<%s,NV=%d,%s,%s,U=%d,MINB=%d,dynamic>", sizeof(VecT) == 16 ? "float4" : "float", NV,
-                  mode == MODE_WEIGHTED ? "weighted" : "unweighted",
-                  src == SRC_PEERS ? "SRC_PEERS" : (src == SRC_TWO ? "SRC_TWO" : "SRC_ONE"), U, DYN_MINB);
-#define CB_STREAM_DYN(M, S)                                                                               \
-  do {                                                                                                    \
-    constexpr auto K = stream_kernel<VecT, NV, M, false, S, U, DYN_MINB, PREFETCH, HINT, true>;               \
-    const unsigned gp = (unsigned)persistent_grid<K>();                                                   \
-    K<<<gd < gp ? gd : gp, 256, 0, stream>>>(p);                                                            \
-  } while (0)
-      if (mode == MODE_WEIGHTED) {
-        if (src == SRC_PEERS) CB_STREAM_DYN(MODE_WEIGHTED, SRC_PEERS);
-        else if (src == SRC_TWO) CB_STREAM_DYN(MODE_WEIGHTED, SRC_TWO);
-        else CB_STREAM_DYN(MODE_WEIGHTED, SRC_ONE);
-      } else {
-        if (src == SRC_PEERS) CB_STREAM_DYN(MODE_UNWEIGHTED, SRC_PEERS);
-        else if (src == SRC_TWO) CB_STREAM_DYN(MODE_UNWEIGHTED, SRC_TWO);
-        else CB_STREAM_DYN(MODE_UNWEIGHTED, SRC_ONE);
-      }
-#undef CB_STREAM_DYN
-      CB_LAUNCH_CHECK();
-      return COGDL_B200_OK;
-    }
-  }
   note_kernel("cogdl_b200::stream_kernel<%s,NV=%d,%s%s,%s,U=%d,MINB=%d%s%s>", sizeof(VecT) == 16 ? "float4" : "float", NV,
               mode == MODE_MULTIHEAD ? "multihead" : (mode == MODE_WEIGHTED ? "weighted" : "unweighted"),
               (mode == MODE_MULTIHEAD && p.perm) ? "+perm" : "",

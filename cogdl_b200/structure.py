@@ -82,7 +82,6 @@ class HubPlan:
             self.hub_rows = torch.empty(max(n_hub, 1), dtype=torch.int32, device=dev)
             self.chunks = torch.empty(max(2 * n_chunks, 2), dtype=torch.int32, device=dev)
             self.counters = torch.zeros(max(n_chunks, 1), dtype=torch.int32, device=dev)
-            self.ticket = torch.zeros(2, dtype=torch.int32, device=dev)   # persistent row-stream form (zero between launches)
             if self.seg_cost > 0 and n_segs > 0:
                 self.segs = torch.empty(2 * n_segs, dtype=torch.int32, device=dev)
                 self.edge_row = torch.empty(int(nnz), dtype=torch.int32, device=dev)
@@ -116,7 +115,6 @@ class HubPlan:
         s.counters = self.counters.data_ptr()
         s.n_empty_rows = self.n_empty_rows
         s.hub_degrees_host = self.hub_degrees_host
-        s.ticket = self.ticket.data_ptr()
         if self.segs is not None:
             s.seg_cost, s.n_segs = self.seg_cost, self.n_segs
             s.segs, s.edge_row = self.segs.data_ptr(), self.edge_row.data_ptr()

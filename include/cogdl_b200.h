@@ -104,10 +104,6 @@ typedef struct cogdl_b200_hub_plan {
    * as many blocks / clusters as there are rows in a tier.  NULL => such ops treat every hub row
    * with the per-warp tier. */
   const int32_t *hub_degrees_host;
-  /* Optional (ABI 5): two ints of device memory, zero on entry, left zero on exit -- work-ticket and retirement
-   * counters of the PERSISTENT form of the row-stream kernels (grid = resident warp slots; a warp draws its next
-   * item from ticket[0] instead of retiring).  NULL => one warp per item.  Per-stream scratch like `counters`. */
-  int32_t *ticket;
 } cogdl_b200_hub_plan_t;
 
 /* Layout self-check for bindings that mirror the struct (ctypes, cgo, JNI): writes sizeof(cogdl_b200_hub_plan_t)

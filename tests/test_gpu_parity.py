@@ -403,3 +403,64 @@ def test_errors_are_raised_not_swallowed(dev):
     lib = cogdl_b200._cabi.load()
     assert lib.cogdl_b200_spmm_csr_f32(None, None, None, None, None, 5, 4, None, None) == cogdl_b200._cabi.EINVAL
     assert "null pointer" in cogdl_b200._cabi.last_error()
+
+
+# ------------------------------------------------------------------------------------ launch-shape knobs
+def _with_tuning(env, fn):
+    """Run fn() with experiment knobs set (environment + cogdl_b200_reload_tuning), then restore the defaults."""
+    import os
+
+    from cogdl_b200 import _cabi
+
+    old = {k: os.environ.get(k) for k in env}
+    try:
+        os.environ.update({k: str(v) for k, v in env.items()})
+        _cabi.load().cogdl_b200_reload_tuning()
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        _cabi.load().cogdl_b200_reload_tuning()
+
+
+@pytest.mark.parametrize("F", [128, 40, 256])
+def test_stream_block_size_is_a_launch_parameter_only(dev, F):
+    """Threads per block of the row-stream kernels (default 128) changes which warp slots are busy, never the
+    arithmetic: every block size gives the same bits (and the oracle's on unsplit rows)."""
+    from cogdl_b200.operators._raw import spmm_raw
+
+    rp, ci, n_cols = case("two_hubs")
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((n_cols, F)).astype(np.float32)
+    val = rng.random(ci.shape[0]).astype(np.float32)
+    st = structure(rp, ci, n_cols, dev, chunk=64)
+    xd, vd = T(X, dev), T(val, dev)
+    y0 = spmm_raw(st, vd, xd)
+    ref = oracle.spmm_csr(rp, ci, val, X)
+    unsplit = np.diff(rp) <= 64
+    assert np.array_equal(y0.cpu().numpy()[unsplit], ref[unsplit]) and rel(y0.cpu().numpy(), ref) <= TOL
+    for block in (256, 64, 32):
+        y = _with_tuning({"COGDL_B200_STREAM_BLOCK": block}, lambda: spmm_raw(st, vd, xd))
+        assert torch.equal(y, y0), f"block={block}"
+    assert int(st.plan.counters.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("H", [8, 4, 1])
+def test_edge_softmax_warps_per_block_is_a_launch_parameter_only(dev, H):
+    from cogdl_b200.operators._raw import edge_softmax_bwd_raw, edge_softmax_fwd_raw
+
+    rp, ci, n_cols = case("two_hubs")
+    rng = np.random.default_rng(22)
+    e = T((rng.standard_normal((ci.shape[0], H)) * 3).astype(np.float32), dev)
+    g = T(rng.standard_normal((ci.shape[0], H)).astype(np.float32), dev)
+    st = structure(rp, ci, n_cols, dev, chunk=64)
+    y0 = edge_softmax_fwd_raw(st, e)
+    b0 = edge_softmax_bwd_raw(st, y0, g)
+    assert np.allclose(y0.cpu().numpy(), oracle.edge_softmax_fwd(rp, e.cpu().numpy()), rtol=1e-5, atol=1e-7)
+    for warps in (8, 4):
+        y, b = _with_tuning({"COGDL_B200_ES_WARPS": warps},
+                            lambda: (edge_softmax_fwd_raw(st, e), edge_softmax_bwd_raw(st, y0, g)))
+        assert torch.equal(y, y0) and torch.equal(b, b0), f"warps={warps}"
