@@ -454,12 +454,12 @@ def test_edge_softmax_warps_per_block_is_a_launch_parameter_only(dev, H):
 
     rp, ci, n_cols = case("two_hubs")
     rng = np.random.default_rng(22)
-    e = T((rng.standard_normal((ci.shape[0], H)) * 3).astype(np.float32), dev)
+    e = T(np.clip(rng.standard_normal((ci.shape[0], H)) * 3, -10, 10).astype(np.float32), dev)
     g = T(rng.standard_normal((ci.shape[0], H)).astype(np.float32), dev)
     st = structure(rp, ci, n_cols, dev, chunk=64)
     y0 = edge_softmax_fwd_raw(st, e)
     b0 = edge_softmax_bwd_raw(st, y0, g)
-    assert np.allclose(y0.cpu().numpy(), oracle.edge_softmax_fwd(rp, e.cpu().numpy()), rtol=1e-5, atol=1e-7)
+    assert rel(y0.cpu().numpy(), oracle.edge_softmax_fwd(rp, e.cpu().numpy())) <= TOL
     for warps in (8, 4):
         y, b = _with_tuning({"COGDL_B200_ES_WARPS": warps},
                             lambda: (edge_softmax_fwd_raw(st, e), edge_softmax_bwd_raw(st, y0, g)))
