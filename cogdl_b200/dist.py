@@ -141,6 +141,8 @@ class PartitionedSpMM:
         nccl = dist.get_backend(group) == "nccl"
         if mode is None:
             mode = "p2p" if (device.type == "cuda" and nccl and part.col_peer is not None) else "nccl"
+        if mode not in ("p2p", "nccl"):
+            raise ValueError(f"PartitionedSpMM mode must be 'p2p' or 'nccl', got {mode!r} (the push form is dist.PushSpMM)")
         self.mode = mode
         self.x_local = None
         self._symm = None
