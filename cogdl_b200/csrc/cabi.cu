@@ -10,7 +10,6 @@
 #include <cstring>
 #include <map>
 #include <mutex>
-#include <string>
 
 namespace cogdl_b200 {
 
@@ -35,8 +34,12 @@ void note_kernel(const char *fmt, ...) {
   va_end(ap);
 }
 
+// keyed by the (string-literal) name itself: no allocation on the lookup path
+struct CStrLess {
+  bool operator()(const char *a, const char *b) const { return strcmp(a, b) < 0; }
+};
 static std::mutex g_tuning_mu;
-static std::map<std::string, int> g_tuning;
+static std::map<const char *, int, CStrLess> g_tuning;
 int tuning(const char *env_name, int dflt) {
   std::lock_guard<std::mutex> lock(g_tuning_mu);
   auto it = g_tuning.find(env_name);
