@@ -51,6 +51,7 @@ SIGNATURES = {
     "cogdl_b200_launch_count": (_i64, []),
     "cogdl_b200_last_kernel": (ctypes.c_char_p, []),
     "cogdl_b200_reload_tuning": (None, []),
+    "cogdl_b200_tuning_value": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "cogdl_b200_hub_plan_layout": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
     "cogdl_b200_hub_plan_count": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "cogdl_b200_hub_plan_fill": (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -162,6 +162,17 @@ extern "C" const char *cogdl_b200_last_kernel(void) { return g_kernel; }
 
 extern "C" void cogdl_b200_reload_tuning(void) { tuning_reload(); }
 
+// What a knob currently resolves to (cached value if the library has read it, else the environment, else dflt).
+// Never inserts: `name` may be a temporary of the caller.
+extern "C" int cogdl_b200_tuning_value(const char *name, int dflt) {
+  if (!name) return dflt;
+  std::lock_guard<std::mutex> lock(g_tuning_mu);
+  auto it = g_tuning.find(name);
+  if (it != g_tuning.end()) return it->second;
+  const char *e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 extern "C" int cogdl_b200_hub_plan_layout(int64_t *out, int n) {
   typedef cogdl_b200_hub_plan_t P;
   const int64_t v[] = {(int64_t)sizeof(P), offsetof(P, chunk_edges), offsetof(P, n_hub_rows), offsetof(P, n_chunks),

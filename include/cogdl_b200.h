@@ -61,6 +61,8 @@ COGDL_B200_API const char *cogdl_b200_last_kernel(void);
 /* Experiment knobs (environment variables COGDL_B200_*: kernel variants, tile floors) are read once and cached;
  * this drops the cache so that a tuning sweep can change them inside one process.  Not needed in normal use. */
 COGDL_B200_API void cogdl_b200_reload_tuning(void);
+/* What the knob `name` currently resolves to: the cached value, else the environment, else `dflt`. */
+COGDL_B200_API int cogdl_b200_tuning_value(const char *name, int dflt);
 
 /* ---------------------------------------------------------------------------------------
  * Hub plan: how rows with more than `chunk_edges` edges are cut into fixed-size edge chunks

@@ -335,3 +335,28 @@ def test_bf16x3_split_gemm_numerics_emulated():
     assert (np.abs(acc - ref) / scale).max() <= 5e-7
     plain = bf16(A).astype(np.float64) @ bf16(W).T.astype(np.float64)
     assert (np.abs(plain - ref) / scale).max() > 1e-4
+
+
+def test_tuning_knobs_follow_the_environment_after_reload():
+    """Experiment knobs (COGDL_B200_*) are cached by the library; cogdl_b200_reload_tuning() drops the cache so a sweep
+    (tools/ab_stream.py) or a test can change them inside one process and restore the defaults afterwards."""
+    import os
+
+    from cogdl_b200 import _cabi
+
+    lib = _cabi.load()
+    name = b"COGDL_B200_STREAM_BLOCK"
+    old = os.environ.pop(name.decode(), None)
+    try:
+        lib.cogdl_b200_reload_tuning()
+        assert lib.cogdl_b200_tuning_value(name, 128) == 128          # unset -> the caller's default
+        os.environ[name.decode()] = "64"
+        assert lib.cogdl_b200_tuning_value(name, 128) == 64
+        os.environ.pop(name.decode())
+        lib.cogdl_b200_reload_tuning()
+        assert lib.cogdl_b200_tuning_value(name, 128) == 128
+        assert lib.cogdl_b200_tuning_value(None, 7) == 7
+    finally:
+        if old is not None:
+            os.environ[name.decode()] = old
+        lib.cogdl_b200_reload_tuning()
