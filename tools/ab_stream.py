@@ -1,16 +1,19 @@
 """One-process A/B of the row-stream kernels' launch shapes on a B200 (CUDA events, L2 flushed between runs):
 
-   python tools/ab_stream.py [safe|dynamic|all]  ->  gpurun_out/ab_stream.jsonl  (one JSON line per configuration)
+   python tools/ab_stream.py  ->  gpurun_out/ab_stream_all.jsonl  (one JSON line per configuration)
 
   block     COGDL_B200_STREAM_BLOCK in {256, 128, 64, 32}: threads per block of the one-warp-per-item kernel (same SASS,
             launch parameter only; smaller blocks hand a retired warp's slot to new work sooner)
-  dynamic   COGDL_B200_STREAM_DYNAMIC=1: persistent form, items drawn from the plan's ticket counter
+  variant   COGDL_B200_SPMM_VARIANT: unroll depth / resident blocks of the lean SpMM kernel
+  chunk     edges per hub chunk of the plan
+  es_warps  COGDL_B200_ES_WARPS in {8, 4, 2}: warps per block of the edge-softmax 512-float-tile kernel
   seg       segment cost of the hub plan (rows + edges per warp item)
 
 Every configuration's output is compared BIT FOR BIT with the default configuration's (the per-row arithmetic order
-does not depend on the launch shape), and the plan's arrival / ticket counters must be zero afterwards.  Knobs are
+does not depend on the launch shape), and the plan's arrival counters must be zero afterwards.  Knobs are
 switched inside one process through cogdl_b200_reload_tuning().  Results are flushed line by line, so a run that is
-cut off keeps what it measured."""
+cut off keeps what it measured.  (profiles/r02s_ab_launch_shapes.md is a run of this tool; at that time it also timed a
+persistent ticket-counter form of the kernel, since removed.)"""
 import json
 import os
 import statistics
@@ -25,7 +28,7 @@ from cogdl_b200 import _cabi, synth  # noqa: E402
 from cogdl_b200.operators._raw import mhspmm_raw, spmm_raw  # noqa: E402
 from cogdl_b200.structure import CSRStructure  # noqa: E402
 
-what = sys.argv[1] if len(sys.argv) > 1 else "all"
+what = "all"
 dev = torch.device("cuda")
 os.makedirs("gpurun_out", exist_ok=True)
 out = open(os.path.join("gpurun_out", f"ab_stream_{what}.jsonl"), "a")
@@ -40,9 +43,8 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def knobs(block=256, dynamic=0, variant=7):
+def knobs(block=256, variant=7):
     os.environ["COGDL_B200_STREAM_BLOCK"] = str(block)
-    os.environ["COGDL_B200_STREAM_DYNAMIC"] = str(dynamic)
     os.environ["COGDL_B200_SPMM_VARIANT"] = str(variant)
     _cabi.load().cogdl_b200_reload_tuning()
 
@@ -63,14 +65,14 @@ def timed(fn, reps):
 
 
 def sweep(tag, st_by_seg, fn_of_st, shapes, reps):
-    """shapes: list of (block, dynamic).  Reference output = first seg, block 256, dynamic 0."""
+    """shapes: list of (block, _, variant?).  Reference output = first seg, first shape."""
     ref = None
     for seg, st in st_by_seg.items():
         for shape in shapes:
             block, dyn = shape[0], shape[1]
             variant = shape[2] if len(shape) > 2 else 7
             try:
-                knobs(block, dyn, variant)
+                knobs(block, variant)
                 y = fn_of_st(st)
                 torch.cuda.synchronize()
                 if ref is None:
@@ -78,17 +80,16 @@ def sweep(tag, st_by_seg, fn_of_st, shapes, reps):
                 same = bool(torch.equal(y, ref))      # segments only group whole rows; hub chunks (64 edges) are the same
                 close = float((y - ref).abs().max() / ref.abs().max())
                 med, mn = timed(lambda: fn_of_st(st), reps)
-                clean = int(st.plan.counters.abs().sum()) == 0 and int(st.plan.ticket.abs().sum()) == 0
-                emit(case=tag, seg=seg, block=block, dynamic=dyn, variant=variant, median_us=round(med, 1), min_us=round(mn, 1),
+                clean = int(st.plan.counters.abs().sum()) == 0
+                emit(case=tag, seg=seg, block=block, variant=variant, median_us=round(med, 1), min_us=round(mn, 1),
                      bit_identical_to_default=same, max_rel_vs_default=close, counters_clean=clean,
                      kernel=_cabi.last_kernel(), segs=st.plan.n_segs, chunks=st.plan.n_chunks)
             except Exception as ex:  # noqa: BLE001
-                emit(case=tag, seg=seg, block=block, dynamic=dyn, error=f"{type(ex).__name__}: {ex}")
+                emit(case=tag, seg=seg, block=block, error=f"{type(ex).__name__}: {ex}")
     knobs()
 
 
-SAFE, DYN = [(256, 0), (128, 0), (64, 0), (32, 0)], [(256, 0), (256, 1)]
-shapes = DYN if what == "dynamic" else SAFE     # "all": the safe shapes first, the persistent form at the very end
+shapes = [(256, 0), (128, 0), (64, 0), (32, 0)]
 
 # ---- arxiv shape (headline): weighted SpMM, F = 128 / 40 / 256; multi-head SpMM H = 8, F = 128
 n, e = synth.SHAPES["arxiv"]
@@ -102,7 +103,7 @@ emit(case="setup", arxiv_nnz=sts[128].nnz, gpu=torch.cuda.get_device_name(0))
 for F in (128, 40, 256):
     x = torch.randn(n, F, device=dev)
     sweep(f"arxiv_spmm_F{F}", sts if F == 128 else {128: sts[128]}, lambda st: spmm_raw(st, w, x), shapes, 30 if F == 128 else 15)
-    if F == 128 and what != "dynamic":
+    if F == 128:
         # other unroll / occupancy variants of the lean kernel at the two extreme block sizes
         sweep("arxiv_spmm_F128_variants", {128: sts[128]}, lambda st: spmm_raw(st, w, x),
               [(256, 0, 7), (256, 0, 3), (64, 0, 3), (256, 0, 1), (64, 0, 1)], 20)
@@ -114,8 +115,8 @@ for F in (128, 40, 256):
             del stc
     del x
 H = 8
-if what != "dynamic":
-    # ---- edge softmax family (arxiv, H = 8): warps per block of the staged main kernel
+if True:   # ---- edge softmax family
+    # (arxiv, H = 8): warps per block of the staged main kernel
     from cogdl_b200.operators._raw import edge_softmax_bwd_raw, edge_softmax_fwd_raw, gat_attn_bwd_raw  # noqa: E402
 
     st = sts[128]
@@ -144,7 +145,7 @@ if what != "dynamic":
     os.environ["COGDL_B200_ES_WARPS"] = "8"
     _cabi.load().cogdl_b200_reload_tuning()
     del logits, g, hl, hr, att0
-if what != "dynamic":
+if True:
     att = torch.rand(sts[128].nnz, H, device=dev)
     h = torch.randn(n, H, 128, device=dev)
     sweep("arxiv_mhspmm_H8_F128", {128: sts[128]}, lambda st: mhspmm_raw(st, att, h), [s for s in shapes if s[1] == 0], 8)
@@ -158,13 +159,4 @@ del rp, col
 st.plan
 x = torch.randn(n, 128, device=dev)
 sweep("products_spmm_F128", {128: st}, lambda s_: spmm_raw(s_, None, x), shapes, 6)
-emit(case="safe_done" if what != "dynamic" else "done")
-if what == "all":
-    # ---- persistent form last: everything above is already on disk should this part misbehave
-    sweep("products_spmm_F128_dynamic", {128: st}, lambda s_: spmm_raw(s_, None, x), DYN, 6)
-    del x, st
-    for F in (128, 40):
-        x = torch.randn(sts[128].n_rows, F, device=dev)
-        sweep(f"arxiv_spmm_F{F}_dynamic", sts if F == 128 else {128: sts[128]}, lambda st_: spmm_raw(st_, w, x), DYN, 30)
-        del x
-    emit(case="done")
+emit(case="done")
