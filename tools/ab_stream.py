@@ -43,9 +43,13 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def knobs(block=256, variant=7):
-    os.environ["COGDL_B200_STREAM_BLOCK"] = str(block)
-    os.environ["COGDL_B200_SPMM_VARIANT"] = str(variant)
+def knobs(block=None, variant=None):
+    """Set the launch-shape knobs (None = the library's default)."""
+    for name, v in (("COGDL_B200_STREAM_BLOCK", block), ("COGDL_B200_SPMM_VARIANT", variant)):
+        if v is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = str(v)
     _cabi.load().cogdl_b200_reload_tuning()
 
 
