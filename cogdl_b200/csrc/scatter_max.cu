@@ -286,14 +286,8 @@ __global__ void __launch_bounds__(256) scatter_max_stream_kernel(const SmaxParam
   }
 }
 
-static bool smax_stream_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("COGDL_B200_SMAX_STREAM");
-    v = e ? atoi(e) : 1;   // bit-exact either way; products shape F=256: 11.38 ms vs 11.52 ms (row per warp)
-  }
-  return v != 0;
-}
+// bit-exact either way; products shape F=256: 11.38 ms (row-stream form) vs 11.52 ms (row per warp)
+static bool smax_stream_enabled() { return tuning("COGDL_B200_SMAX_STREAM", 1) != 0; }
 
 template <int NV>
 static int launch_smax_stream(const SmaxParams &p, cudaStream_t stream) {

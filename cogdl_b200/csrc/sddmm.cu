@@ -206,15 +206,9 @@ __global__ void __launch_bounds__(256) sddmm_stream_kernel(const SddmmParams p) 
   }
 }
 
-static bool sddmm_stream_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("COGDL_B200_SDDMM_STREAM");
-    v = e ? atoi(e) : 0;   // measured on B200 (arxiv shape): 189 vs 175 us (F=128), 1377 vs 1317 us (H=8,F=128):
-                           // gathering both operands costs more LSU traffic than the row form saves -> off
-  }
-  return v != 0;
-}
+// measured on B200 (arxiv shape): 189 vs 175 us (F=128), 1377 vs 1317 us (H=8,F=128): gathering both operands
+// costs more LSU traffic than the row form saves -> off by default
+static bool sddmm_stream_enabled() { return tuning("COGDL_B200_SDDMM_STREAM", 0) != 0; }
 
 template <int NV>
 static int launch_sddmm_stream(const SddmmParams &p, cudaStream_t stream) {
