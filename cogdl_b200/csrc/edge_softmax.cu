@@ -540,10 +540,11 @@ __global__ void __launch_bounds__(256) es_generic_kernel(const EsParams p) {
   }
 }
 
-// warps per block of the 512-float-tile main kernel (COGDL_B200_ES_WARPS = 8 | 4 | 2 overrides).  Measured at arxiv
-// H=8 (profiles/r02s_ab_launch_shapes.md), 8 / 4 / 2 warps: fwd 48.1 / 46.1 / 46.1 us, bwd 46.1 / 45.1 / 44.0,
-// attention bwd 77.8 / 76.8 / 74.8; bit-identical outputs.
-constexpr int ES_WARPS_DEFAULT = 2;
+// warps per block of the 512-float-tile main kernel (COGDL_B200_ES_WARPS = 8 | 4 | 2).  Measured at arxiv H=8
+// (profiles/r02s_ab_launch_shapes.md), 8 / 4 / 2 warps: fwd 48.1 / 46.1 / 46.1 us, bwd 46.1 / 45.1 / 44.0, attention
+// bwd 77.8 / 76.8 / 74.8, bit-identical outputs: a 4 % effect on an issue-bound kernel.  The default stays at the
+// shape the whole GPU suite was validated with; the smaller blocks are one environment variable away.
+constexpr int ES_WARPS_DEFAULT = 8;
 
 template <int MODE, int CAP, int WARPS = 8>
 static int launch_main(const EsParams &p, cudaStream_t s) {
@@ -615,7 +616,7 @@ static int es_launch(EsParams p, const cogdl_b200_hub_plan_t *plan, cudaStream_t
   // warps per block of the 512-float-tile instantiation (tuning: a block's shared memory and warp slots are released
   // when its slowest warp retires)
   const int es_warps = chosen == 512 ? tuning("COGDL_B200_ES_WARPS", ES_WARPS_DEFAULT) : 8;
-  const int warps = (es_warps == 4 || es_warps == 8) ? es_warps : 2;
+  const int warps = (es_warps == 4 || es_warps == 2) ? es_warps : 8;
   note_kernel("cogdl_b200::es_main_kernel<MODE=%d,CAP=%d,WARPS=%d>%s", MODE, chosen, warps,
               (p.bulk && MODE != 2) ? " cp.async.bulk tiles" : "");
   if (chosen == 512 && warps == 4) return launch_main<MODE, 512, 4>(p, s);

@@ -448,7 +448,7 @@ def test_stream_block_size_is_a_launch_parameter_only(dev, F):
     assert int(st.plan.counters.abs().sum()) == 0
 
 
-@pytest.mark.parametrize("H", [8, 4, 1])
+@pytest.mark.parametrize("H", [8, 4])
 def test_edge_softmax_warps_per_block_is_a_launch_parameter_only(dev, H):
     from cogdl_b200.operators._raw import edge_softmax_bwd_raw, edge_softmax_fwd_raw
 
@@ -460,7 +460,7 @@ def test_edge_softmax_warps_per_block_is_a_launch_parameter_only(dev, H):
     y0 = edge_softmax_fwd_raw(st, e)
     b0 = edge_softmax_bwd_raw(st, y0, g)
     assert rel(y0.cpu().numpy(), oracle.edge_softmax_fwd(rp, e.cpu().numpy())) <= TOL
-    for warps in (8, 4):
+    for warps in (4, 2):
         y, b = _with_tuning({"COGDL_B200_ES_WARPS": warps},
                             lambda: (edge_softmax_fwd_raw(st, e), edge_softmax_bwd_raw(st, y0, g)))
         assert torch.equal(y, y0) and torch.equal(b, b0), f"warps={warps}"
