@@ -164,3 +164,37 @@ def _push_worker(rank, world, port, out_dir, weighted):
 def test_push_form_host_logic(tmp_path, world, weighted):
     mp.spawn(_push_worker, args=(world, _free_port(), str(tmp_path), weighted), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"push_ok{r}") for r in range(world))
+
+
+def _push_edge_worker(rank, world, port, out_dir):
+    """No boundary edges at all (every column inside the row's own range) and an empty rank: the exchange carries
+    zero rows and the combined block is the interior block."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from cogdl_b200 import dist as cdist, synth
+
+        n, e, F = 1200, 9000, 4
+        rp, col = synth.powerlaw_csr(n, e, seed=9, locality=(2, 0.0), self_loops=False)   # two ranges of 600 nodes, no crossing edge
+        bounds = [0, 600, 1200, 1200][: world + 1] if world == 3 else [0, 600, 1200]     # world 3: rank 2 owns nothing
+        lo, hi = bounds[rank], bounds[rank + 1]
+        X = torch.randn(n, F, generator=torch.Generator().manual_seed(1))
+        part = cdist.PushPartition.from_global_csr(rp, col, None, rank, world, bounds)
+        assert part.n_brow == 0 and part.n_recv == 0 and sum(part.send_counts) == 0
+        assert part.n_local == hi - lo and part.c_rowptr.numel() == part.n_local + 1
+        ps = cdist.PushSpMM(part, torch.device("cpu"))
+        R = ps.reduce_scatter(torch.zeros((0, F)), F)
+        assert R.shape == (0, F)
+        if part.n_local:
+            y = oracle.spmm_csr(part.c_rowptr.numpy(), part.c_col.numpy(), None, X[lo:hi].numpy())
+            assert np.array_equal(y, oracle.spmm_csr(rp.numpy(), col.numpy(), None, X.numpy())[lo:hi])   # same order: exact
+        open(os.path.join(out_dir, f"edge_ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_push_form_without_boundary_and_with_an_empty_rank(tmp_path, world):
+    mp.spawn(_push_edge_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"edge_ok{r}") for r in range(world))
